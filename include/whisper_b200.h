@@ -1,0 +1,158 @@
+/* whisper_b200.h -- C ABI of libwhisper_b200.so
+ *
+ * B200-native (sm_100a) drop-in for ONE path of paiml/whisper.apr: batched log-mel
+ * extraction over 30 s chunks followed by the Whisper encoder forward pass.
+ *
+ * The reference has no FFI boundary for this path (its only extern surface is
+ * wasm-bindgen); the boundary it offers is its Rust public API.  Every entry point
+ * below is shaped 1:1 after the Rust signature it replaces (cited as file:line,
+ * relative to the reference checkout) so that a thin `extern "C"` crate can bind it
+ * (INTEGRATION.md shows the binding).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - Status: 0 OK; 1 Audio, 2 Model, 3 Format mirror WhisperError::{Audio,Model,Format}
+ *     (src/error.rs:6-44); 4 = CUDA failure.  wb_last_error() returns the message
+ *     (thread-local), like WhisperError's Display.
+ *   - Caller owns every host buffer.  The library owns device memory behind wb_model.
+ *   - All calls are synchronous with respect to their host outputs.  The *_dev entry
+ *     points take DEVICE pointers, enqueue on the model's stream and do not synchronise.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with
+ *     WB_ERR_CUDA.
+ */
+#ifndef WHISPER_B200_H
+#define WHISPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB_OK 0
+#define WB_ERR_AUDIO 1
+#define WB_ERR_MODEL 2
+#define WB_ERR_FORMAT 3
+#define WB_ERR_CUDA 4
+
+typedef struct wb_model wb_model;
+
+/* ModelConfig (src/model/mod.rs:35-62) as read from the .apr header
+ * (AprHeader::to_model_config, src/format/mod.rs:249-279), plus the file's quantization byte. */
+typedef struct wb_config {
+  uint32_t model_type;
+  uint32_t n_vocab;
+  uint32_t n_audio_ctx;
+  uint32_t n_audio_state;
+  uint32_t n_audio_head;
+  uint32_t n_audio_layer;
+  uint32_t n_text_ctx;
+  uint32_t n_text_state;
+  uint32_t n_text_head;
+  uint32_t n_text_layer;
+  uint32_t n_mels;
+  uint32_t quantization; /* 0 F32, 1 F16 (unsupported, as in the reference), 2 Int8, 3 Int4 */
+  uint32_t has_filterbank;
+  uint32_t n_tensors;
+} wb_config;
+
+/* Output element type of the fused batch entry point. */
+typedef enum wb_dtype { WB_F32 = 0, WB_BF16 = 1 } wb_dtype;
+
+/* ---- library ---------------------------------------------------------------------- */
+const char* wb_version(void);
+/* WhisperError Display (src/error.rs).  Thread-local; valid until the next failing call. */
+const char* wb_last_error(void);
+/* parallel::thread_count (src/parallel.rs:155-170) -> number of visible CUDA devices. */
+int wb_device_count(void);
+
+/* ---- model ------------------------------------------------------------------------ */
+/* WhisperApr::load_from_apr (src/lib.rs:673-754) restricted to what this path needs:
+ * AprReader::new (src/format/mod.rs:484-522), header -> config, load_encoder_weights
+ * (src/lib.rs:757-841, 931-993), read_mel_filterbank -> MelFilterbank::from_apr_data
+ * (src/lib.rs:738-741; falls back to MelFilterbank::new's HTK filters when the file has
+ * none, src/lib.rs:297-298).  Missing tensors keep their defaults, lengths are clamped,
+ * exactly as the reference loader does.  Int8 / Int4 weights stay packed on the host side of
+ * the upload and are expanded on the device.  `device` is the CUDA ordinal. */
+int wb_model_from_apr(const uint8_t* bytes, size_t n_bytes, int device, wb_model** out);
+/* WhisperApr::config (src/lib.rs:330-333). */
+int wb_model_config(const wb_model* m, wb_config* out);
+void wb_model_free(wb_model* m);
+/* parallel::configure_thread_pool (src/parallel.rs:34-60) analogue: the stream the model's
+ * kernels are enqueued on (a cudaStream_t; NULL restores the model's own stream). */
+int wb_model_set_stream(wb_model* m, void* cuda_stream);
+/* Upper bound on chunks processed per device pass (workspace is sized for it). */
+int wb_model_set_max_batch(wb_model* m, int max_chunks);
+
+/* ---- mel -------------------------------------------------------------------------- */
+/* MelFilterbank::compute (src/audio/mel.rs:233-310).  out: [n_frames][n_mels] f32, frame-major,
+ * capacity out_capacity floats; *n_frames_out = (n - 400) / hop + 1, or 0 for n < 400 / n == 0
+ * (then nothing is written).  hop == 0 -> WB_ERR_AUDIO ("hop_length must be positive"). */
+int wb_mel_compute(const wb_model* m, const float* audio, size_t n, size_t hop, float* out, size_t out_capacity,
+                   size_t* n_frames_out);
+/* WhisperApr::compute_mel (src/lib.rs:407-443): pad/truncate to 480000 samples, mel, pad the
+ * frame axis to 3000 with -1.0.  out: [3000][n_mels] f32.  (n_mels comes from the model, not the
+ * reference's hard-coded 80 -- see DESIGN.md.) */
+int wb_compute_mel(const wb_model* m, const float* audio, size_t n, float* out);
+/* Batched compute_mel: `audio` is B chunks of exactly 480000 samples, contiguous. */
+int wb_compute_mel_batch(const wb_model* m, const float* audio, int B, float* out);
+
+/* ---- encoder ---------------------------------------------------------------------- */
+/* WhisperApr::encode == Encoder::forward_mel (src/lib.rs:446-449, src/model/encoder.rs:566-581).
+ * mel: [n_frames][n_mels] f32 (mel_len floats).  out: [S][d] f32 with
+ * S = (n_frames - 1) / 2 + 1; *seq_len_out = S.  mel_len % n_mels != 0 -> WB_ERR_MODEL
+ * ("mel size .. not divisible by n_mels"); S > n_audio_ctx -> WB_ERR_MODEL
+ * ("sequence length .. exceeds max .."), as encoder.rs:450-461. */
+int wb_encode(const wb_model* m, const float* mel, size_t mel_len, float* out, size_t out_capacity, size_t* seq_len_out);
+/* Encoder::forward_batch_padded (src/model/encoder.rs:625-660): B mels of possibly different
+ * lengths -> out [B][max_seq][d] zero padded, seq_lens[B], *max_seq_out.  out_capacity in floats.
+ * Encoder::forward_batch (encoder.rs:599-608) is the same call read back per item. */
+int wb_encode_batch(const wb_model* m, const float* const* mels, const size_t* mel_lens, int B, float* out,
+                    size_t out_capacity, size_t* seq_lens, size_t* max_seq_out);
+
+/* ---- fused hot path --------------------------------------------------------------- */
+/* transcribe_batch_optimized steps 1-2 (src/lib.rs:1162-1170): compute_mel per item then
+ * Encoder::forward_batch.  audio[i] has n_samples[i] samples (padded/truncated to 30 s as
+ * compute_mel does).  out: [B][1500][d] in out_dtype (WB_F32 as the reference, or WB_BF16).
+ * This is the measured entry point (bench.py `e2e`): host buffers in, host buffer out. */
+int wb_mel_encode_batch(const wb_model* m, const float* const* audio, const size_t* n_samples, int B, void* out,
+                        wb_dtype out_dtype);
+/* Same work with inputs already resident in HBM: d_audio [B][480000] f32 (device), d_out
+ * [B][1500][d] (device).  Enqueues on the model's stream; does not synchronise. */
+int wb_mel_encode_batch_dev(const wb_model* m, const float* d_audio, int B, void* d_out, wb_dtype out_dtype);
+/* Device-resident pieces of the same path, for per-kernel measurement. */
+int wb_compute_mel_batch_dev(const wb_model* m, const float* d_audio, int B, float* d_mel_out);
+int wb_encode_batch_dev(const wb_model* m, const float* d_mel, int B, void* d_out, wb_dtype out_dtype);
+/* Block until the model's stream is idle. */
+int wb_sync(const wb_model* m);
+
+/* ---- chunking --------------------------------------------------------------------- */
+/* audio::split_into_chunks (src/audio/batch.rs:219-240).  Writes up to `capacity` (start,len)
+ * pairs; returns the number of chunks the reference would produce (may exceed capacity). */
+size_t wb_split_into_chunks(size_t n_samples, size_t chunk_size, size_t overlap, size_t* starts, size_t* lens,
+                            size_t capacity);
+/* BatchMelResult::to_padded_tensor (src/audio/batch.rs:107-127): [B][n_mels][max_frames], zero padded. */
+int wb_to_padded_tensor(const float* const* mels, const size_t* frame_counts, int B, size_t n_mels, size_t max_frames,
+                        float* out);
+
+/* ---- test hooks (not part of the reference surface) ------------------------------- */
+/* Host restatement of the kernel's FFT factorisation: P[201] = |rfft400(y)|^2.  No GPU needed. */
+void wb_debug_fft400_power_host(const float* y400, float* p201);
+/* One GEMM through the tcgen05 kernel: out = epilogue(alpha * A[M][K] W[N][K]^T + bias), host buffers
+ * (A, W as f32, rounded to bf16 on upload; out as f32).  epilogue: see GemmEpilogue in wb_internal.h. */
+int wb_debug_gemm(int device, const float* A, const float* W, const float* bias, const float* resid_or_pe, int M, int N,
+                  int K, int epilogue, float alpha, float* out);
+/* One attention call: qkv f32 [B][S][3d] (rounded to bf16) -> out f32 [B][S][d]. */
+int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_heads, float* out);
+/* Encoder::forward_mel truncated after n_layers blocks (n_layers < 0: all), with or without ln_post: stage-wise parity. */
+int wb_debug_encode(const wb_model* m, const float* mel, size_t mel_len, int n_layers, int ln_post, float* out,
+                    size_t out_capacity);
+/* Number of CUDA kernels this library has launched in this process (all models). */
+long long wb_launch_count(void);
+/* LayerNorm rows: x f32 [rows][d] -> out f32 (exact f32 result) */
+int wb_debug_layernorm(int device, const float* x, const float* gamma, const float* beta, int rows, int d, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHISPER_B200_H */

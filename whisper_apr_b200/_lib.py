@@ -1,0 +1,103 @@
+"""ctypes binding of libwhisper_b200.so (the C ABI declared in include/whisper_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``make -C whisper_apr_b200/csrc``.
+There is no fallback: if the library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwhisper_b200.so")
+
+WB_OK, WB_ERR_AUDIO, WB_ERR_MODEL, WB_ERR_FORMAT, WB_ERR_CUDA = 0, 1, 2, 3, 4
+WB_F32, WB_BF16 = 0, 1
+
+
+class WbConfig(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "model_type", "n_vocab", "n_audio_ctx", "n_audio_state", "n_audio_head", "n_audio_layer",
+        "n_text_ctx", "n_text_state", "n_text_head", "n_text_layer", "n_mels", "quantization",
+        "has_filterbank", "n_tensors")]
+
+
+_f32p = C.POINTER(C.c_float)
+_szp = C.POINTER(C.c_size_t)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/whisper_b200.h declares
+SIGNATURES = {
+    "wb_version": (C.c_char_p, []),
+    "wb_last_error": (C.c_char_p, []),
+    "wb_device_count": (C.c_int, []),
+    "wb_model_from_apr": (C.c_int, [_vp, C.c_size_t, C.c_int, C.POINTER(_vp)]),
+    "wb_model_config": (C.c_int, [_vp, C.POINTER(WbConfig)]),
+    "wb_model_free": (None, [_vp]),
+    "wb_model_set_stream": (C.c_int, [_vp, _vp]),
+    "wb_model_set_max_batch": (C.c_int, [_vp, C.c_int]),
+    "wb_mel_compute": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t, _szp]),
+    "wb_compute_mel": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "wb_compute_mel_batch": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "wb_encode": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp]),
+    "wb_encode_batch": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, _vp, C.c_size_t, _szp, _szp]),
+    "wb_mel_encode_batch": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, _vp, C.c_int]),
+    "wb_mel_encode_batch_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int]),
+    "wb_compute_mel_batch_dev": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "wb_encode_batch_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int]),
+    "wb_sync": (C.c_int, [_vp]),
+    "wb_split_into_chunks": (C.c_size_t, [C.c_size_t, C.c_size_t, C.c_size_t, _szp, _szp, C.c_size_t]),
+    "wb_to_padded_tensor": (C.c_int, [C.POINTER(_vp), _szp, C.c_int, C.c_size_t, C.c_size_t, _vp]),
+    "wb_debug_fft400_power_host": (None, [_vp, _vp]),
+    "wb_debug_gemm": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp]),
+    "wb_debug_attention": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "wb_debug_encode": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int, _vp, C.c_size_t]),
+    "wb_launch_count": (C.c_longlong, []),
+    "wb_debug_layernorm": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libwhisper_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libwhisper_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C whisper_apr_b200/csrc` "
+                "(or __graft_entry__.build()); there is no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+class WhisperError(RuntimeError):
+    """WhisperError::{Audio, Model, Format} (src/error.rs:6-44) + Cuda."""
+
+    KINDS = {WB_ERR_AUDIO: "Audio", WB_ERR_MODEL: "Model", WB_ERR_FORMAT: "Format", WB_ERR_CUDA: "Cuda"}
+
+    def __init__(self, status: int, message: str):
+        self.status = status
+        self.kind = self.KINDS.get(status, f"status {status}")
+        super().__init__(f"{self.kind} error: {message}")
+
+
+def check(status: int) -> None:
+    if status != WB_OK:
+        raise WhisperError(status, (lib().wb_last_error() or b"").decode("utf-8", "replace"))

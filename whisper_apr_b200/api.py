@@ -1,0 +1,250 @@
+"""Host-side mirror of the reference's public API for the mel + encoder path.
+
+Names, argument meaning and error behaviour follow the Rust items they stand in for
+(paths relative to the reference checkout); all compute goes through the C ABI of
+libwhisper_b200.so -- nothing here computes on the CPU.
+
+  WhisperApr.load_from_apr / config / compute_mel / encode   src/lib.rs:673-754, 330-333, 407-449
+  WhisperApr.mel_filters.compute                              src/audio/mel.rs:233-310
+  WhisperApr.encoder.forward_mel / forward_batch{,_padded}    src/model/encoder.rs:566-660
+  WhisperApr.mel_encode_batch                                 src/lib.rs:1162-1170 (transcribe_batch_optimized steps 1-2)
+  split_into_chunks / BatchMelResult.to_padded_tensor         src/audio/batch.rs:219-240, 107-127
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import WB_BF16, WB_F32, WbConfig, WhisperError, check
+
+N_SAMPLES_30S = 480_000
+N_FRAMES_30S = 3000
+HOP_LENGTH = 160
+N_FFT = 400
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class BatchEncoderOutput:
+    """model/encoder.rs:673-720."""
+    features: np.ndarray          # [batch_size][max_seq_len][d_model], zero padded
+    seq_lengths: list
+    max_seq_len: int
+    batch_size: int
+    d_model: int
+
+    def get(self, batch_idx: int):
+        if batch_idx >= self.batch_size:
+            return None
+        return self.features[batch_idx, : self.seq_lengths[batch_idx]].copy()
+
+    def is_empty(self) -> bool:
+        return self.batch_size == 0
+
+    def total_tokens(self) -> int:
+        return int(sum(self.seq_lengths))
+
+
+class _MelFilters:
+    """MelFilterbank bound to a loaded model (src/audio/mel.rs)."""
+
+    def __init__(self, owner: "WhisperApr"):
+        self._o = owner
+
+    @property
+    def n_mels(self) -> int:
+        return self._o.config.n_mels
+
+    def compute(self, audio, hop_length: int = HOP_LENGTH) -> np.ndarray:
+        """MelFilterbank::compute -> [n_frames][n_mels] f32 (frame-major); empty / short audio -> empty."""
+        audio = _f32(audio).ravel()
+        n = audio.size
+        if n == 0:
+            return np.zeros((0, self.n_mels), np.float32)
+        if hop_length == 0:
+            raise WhisperError(_lib.WB_ERR_AUDIO, "hop_length must be positive")
+        n_frames = (n - N_FFT) // hop_length + 1 if n >= N_FFT else 0
+        out = np.empty((max(n_frames, 0), self.n_mels), np.float32)
+        got = C.c_size_t(0)
+        check(_lib.lib().wb_mel_compute(self._o._h, _ptr(audio), n, hop_length, _ptr(out), out.size, C.byref(got)))
+        return out[: got.value]
+
+
+class _Encoder:
+    """Encoder bound to a loaded model (src/model/encoder.rs)."""
+
+    def __init__(self, owner: "WhisperApr"):
+        self._o = owner
+
+    def forward_mel(self, mel) -> np.ndarray:
+        """Encoder::forward_mel: mel [n_frames][n_mels] (or flat) -> [S][d] f32."""
+        mel = _f32(mel).ravel()
+        cfg = self._o.config
+        cap = (mel.size // max(cfg.n_mels, 1) // 2 + 2) * cfg.n_audio_state
+        out = np.empty(cap, np.float32)
+        s = C.c_size_t(0)
+        check(_lib.lib().wb_encode(self._o._h, _ptr(mel), mel.size, _ptr(out), out.size, C.byref(s)))
+        return out[: s.value * cfg.n_audio_state].reshape(s.value, cfg.n_audio_state).copy()
+
+    def forward_batch_padded(self, batch) -> BatchEncoderOutput:
+        """Encoder::forward_batch_padded."""
+        cfg = self._o.config
+        mels = [_f32(m).ravel() for m in batch]
+        B = len(mels)
+        if B == 0:
+            return BatchEncoderOutput(np.zeros((0, 0, cfg.n_audio_state), np.float32), [], 0, 0, cfg.n_audio_state)
+        ptrs = (C.c_void_p * B)(*[m.ctypes.data for m in mels])
+        lens = (C.c_size_t * B)(*[m.size for m in mels])
+        max_cap = max(m.size // max(cfg.n_mels, 1) // 2 + 2 for m in mels)
+        out = np.empty(B * max_cap * cfg.n_audio_state, np.float32)
+        seq = (C.c_size_t * B)()
+        mx = C.c_size_t(0)
+        check(_lib.lib().wb_encode_batch(self._o._h, ptrs, lens, B, _ptr(out), out.size, seq, C.byref(mx)))
+        feats = out[: B * mx.value * cfg.n_audio_state].reshape(B, mx.value, cfg.n_audio_state).copy()
+        return BatchEncoderOutput(feats, [int(v) for v in seq], int(mx.value), B, cfg.n_audio_state)
+
+    def forward_batch(self, batch):
+        """Encoder::forward_batch: list of [S_i][d] arrays."""
+        o = self.forward_batch_padded(batch)
+        return [o.get(i) for i in range(o.batch_size)]
+
+
+class WhisperApr:
+    """The slice of `WhisperApr` (src/lib.rs:269-449) this library implements."""
+
+    def __init__(self, handle, apr_bytes_keepalive=None):
+        self._h = handle
+        cfg = WbConfig()
+        check(_lib.lib().wb_model_config(self._h, C.byref(cfg)))
+        self.config = cfg
+        self.mel_filters = _MelFilters(self)
+        self.encoder = _Encoder(self)
+
+    # -- construction ------------------------------------------------------------------
+    @classmethod
+    def load_from_apr(cls, data: bytes, device: int = 0) -> "WhisperApr":
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        h = C.c_void_p()
+        st = _lib.lib().wb_model_from_apr(C.c_void_p(arr.ctypes.data if arr.size else 0), arr.size, device, C.byref(h))
+        check(st)
+        return cls(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().wb_model_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(_lib.lib().wb_model_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_max_batch(self, n: int):
+        check(_lib.lib().wb_model_set_max_batch(self._h, n))
+
+    def sync(self):
+        check(_lib.lib().wb_sync(self._h))
+
+    # -- reference API -----------------------------------------------------------------
+    def compute_mel(self, audio) -> np.ndarray:
+        """WhisperApr::compute_mel -> [3000][n_mels] f32."""
+        audio = _f32(audio).ravel()
+        out = np.empty((N_FRAMES_30S, self.config.n_mels), np.float32)
+        check(_lib.lib().wb_compute_mel(self._h, _ptr(audio) if audio.size else None, audio.size, _ptr(out)))
+        return out
+
+    def compute_mel_batch(self, audio) -> np.ndarray:
+        audio = _f32(audio).reshape(-1, N_SAMPLES_30S)
+        out = np.empty((audio.shape[0], N_FRAMES_30S, self.config.n_mels), np.float32)
+        check(_lib.lib().wb_compute_mel_batch(self._h, _ptr(audio), audio.shape[0], _ptr(out)))
+        return out
+
+    def encode(self, mel) -> np.ndarray:
+        """WhisperApr::encode."""
+        return self.encoder.forward_mel(mel)
+
+    def mel_encode_batch(self, audio_batch, out_dtype: str = "f32", out: np.ndarray | None = None) -> np.ndarray:
+        """transcribe_batch_optimized steps 1-2: list of 1-D f32 arrays -> [B][1500][d]."""
+        chunks = [_f32(a).ravel() for a in audio_batch]
+        B = len(chunks)
+        d = self.config.n_audio_state
+        S = (N_FRAMES_30S - 1) // 2 + 1
+        if out_dtype == "f32":
+            out = np.empty((B, S, d), np.float32) if out is None else out
+            code = WB_F32
+        else:
+            out = np.empty((B, S, d), np.uint16) if out is None else out    # raw bf16 bits
+            code = WB_BF16
+        if B == 0:
+            return out
+        ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in chunks])
+        lens = (C.c_size_t * B)(*[c.size for c in chunks])
+        check(_lib.lib().wb_mel_encode_batch(self._h, ptrs, lens, B, _ptr(out), code))
+        return out
+
+    # -- device-pointer entry points (inputs already in HBM) ------------------------------
+    def mel_encode_batch_dev(self, d_audio_ptr: int, B: int, d_out_ptr: int, out_dtype: str = "f32"):
+        check(_lib.lib().wb_mel_encode_batch_dev(self._h, C.c_void_p(d_audio_ptr), B, C.c_void_p(d_out_ptr),
+                                                  WB_F32 if out_dtype == "f32" else WB_BF16))
+
+    def compute_mel_batch_dev(self, d_audio_ptr: int, B: int, d_mel_ptr: int):
+        check(_lib.lib().wb_compute_mel_batch_dev(self._h, C.c_void_p(d_audio_ptr), B, C.c_void_p(d_mel_ptr)))
+
+    def encode_batch_dev(self, d_mel_ptr: int, B: int, d_out_ptr: int, out_dtype: str = "f32"):
+        check(_lib.lib().wb_encode_batch_dev(self._h, C.c_void_p(d_mel_ptr), B, C.c_void_p(d_out_ptr),
+                                              WB_F32 if out_dtype == "f32" else WB_BF16))
+
+    # -- test hook ---------------------------------------------------------------------
+    def debug_encode(self, mel, n_layers: int = -1, ln_post: bool = True) -> np.ndarray:
+        mel = _f32(mel).ravel()
+        cfg = self.config
+        T = mel.size // cfg.n_mels
+        S = (T - 1) // 2 + 1
+        out = np.empty((S, cfg.n_audio_state), np.float32)
+        check(_lib.lib().wb_debug_encode(self._h, _ptr(mel), mel.size, n_layers, int(ln_post), _ptr(out), out.size))
+        return out
+
+
+def split_into_chunks(samples, chunk_size: int, overlap: int):
+    """audio::split_into_chunks (src/audio/batch.rs:219-240)."""
+    samples = _f32(samples).ravel()
+    n = _lib.lib().wb_split_into_chunks(samples.size, chunk_size, overlap, None, None, 0)
+    if n == 0:
+        return []
+    starts = (C.c_size_t * n)()
+    lens = (C.c_size_t * n)()
+    _lib.lib().wb_split_into_chunks(samples.size, chunk_size, overlap, starts, lens, n)
+    return [samples[starts[i]: starts[i] + lens[i]].copy() for i in range(n)]
+
+
+def to_padded_tensor(mels, n_mels: int) -> np.ndarray:
+    """BatchMelResult::to_padded_tensor (src/audio/batch.rs:107-127) -> [B][n_mels][max_frames]."""
+    ms = [_f32(m).reshape(-1, n_mels) for m in mels]
+    B = len(ms)
+    mx = max((m.shape[0] for m in ms), default=0)
+    out = np.zeros((B, n_mels, mx), np.float32)
+    if B == 0 or mx == 0:
+        return out
+    ptrs = (C.c_void_p * B)(*[m.ctypes.data for m in ms])
+    cnt = (C.c_size_t * B)(*[m.shape[0] for m in ms])
+    check(_lib.lib().wb_to_padded_tensor(ptrs, cnt, B, n_mels, mx, _ptr(out)))
+    return out
+
+
+def bf16_bits_to_f32(a: np.ndarray) -> np.ndarray:
+    """View raw bf16 bit patterns (uint16) as float32 values."""
+    return (a.astype(np.uint32) << 16).view(np.float32)

@@ -1,0 +1,99 @@
+// Internal declarations shared by the translation units of libwhisper_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/whisper_b200.h"
+
+namespace wb {
+
+// ---- error plumbing (mirrors WhisperError::{Audio,Model,Format}, src/error.rs:6-44)
+int set_error(int status, const std::string& msg);   // returns status
+const char* last_error();
+#define WB_CUDA_OK(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::wb::set_error(WB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+  } while (0)
+
+// every kernel launch of the library bumps this (bench.py reports it as gpu_launches)
+extern std::atomic<long long> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- GEMM:  out[M][N] = epilogue(alpha * A[M][K] . W[N][K]^T + bias)      (tcgen05 / TMEM / TMA)
+enum GemmEpilogue : int {
+  EPI_BF16 = 0,        // out bf16 = acc*alpha + bias
+  EPI_GELU_BF16 = 1,   // out bf16 = gelu(acc*alpha + bias)
+  EPI_RESID_F32 = 2,   // out f32 += acc*alpha + bias            (residual stream, in place)
+  EPI_GELU_PE_F32 = 3, // out f32 = gelu(acc*alpha + bias) + pe[row_in_batch][n]
+  EPI_F32 = 4,         // out f32 = acc*alpha + bias             (debug / f32 consumers)
+};
+
+struct GemmDesc {
+  // A operand: bf16, viewed as [n_batch][rows_per_batch][K] with arbitrary (16 B aligned) strides.
+  const __nv_bfloat16* A;
+  long long a_row_stride;     // elements between consecutive rows
+  long long a_batch_stride;   // elements between consecutive batch entries
+  int rows_per_batch;
+  int n_batch;
+  // W operand: bf16 [N][K] row-major (the reference's [out][in] layout, attention.rs:33-34)
+  const __nv_bfloat16* W;
+  int N, K;
+  // epilogue
+  int epilogue;
+  float alpha;
+  const float* col_scale;     // [N] per-output-column scale or nullptr (int8/int4 weights)
+  const float* bias;          // [N] or nullptr
+  void* out;                  // row r of batch b lands at row b*out_rows_per_batch + out_row_off + r
+  long long ldc;              // output row pitch, elements
+  int out_rows_per_batch;
+  int out_row_off;
+  const float* pe;            // EPI_GELU_PE_F32: [>=rows_per_batch][N] f32
+};
+int launch_gemm(const GemmDesc& g, cudaStream_t stream);
+int gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+
+// ---- attention: qkv bf16 [B][S][3d] (q | k | v column blocks) -> out bf16 [B][S][d]
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream);
+int attention_init();
+
+// ---- mel
+struct MelTables {                 // device-resident, built at model load
+  const float* window;             // [400] periodic Hann, f32 (mel.rs:215-219)
+  const float* filters;            // [n_mels][201] dense, row-major (mel.rs:96-139)
+  const int* span_lo;              // [n_mels] first non-zero bin
+  const int* span_len;             // [n_mels] bins from first to last non-zero (0 if all-zero row)
+  int n_mels;
+};
+// logmel[b][f][j] = log10(max(E,1e-10)) for f < n_frames; chunk_max_key[b] = ordered-int max.
+int launch_mel_stft(const float* audio, long long audio_stride, const int* n_valid, int padded_len, int hop, int n_frames,
+                    int B, const MelTables& t, float* logmel, int* chunk_max_key, cudaStream_t stream);
+// clamp/scale/pad: out_f32 [B][T_out][m] (optional), out_bf16 [B][T_out+2][m] with zero pad rows (optional)
+int launch_mel_finalize(const float* logmel, const int* chunk_max_key, int n_frames, int T_out, int n_mels, int B,
+                        float* out_f32, __nv_bfloat16* out_bf16_padded, cudaStream_t stream);
+int mel_init();
+
+// ---- elementwise / normalisation
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
+                     float* out_f32, cudaStream_t stream);
+int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+int launch_i8_to_bf16(const int8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+int launch_i4_to_bf16(const uint8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+int launch_i8_to_f32(const int8_t* in, float scale, float* out, size_t n, cudaStream_t stream);
+int launch_i4_to_f32(const uint8_t* in, float scale, float* out, size_t n, cudaStream_t stream);
+// conv weight [out][in][3] (any of f32/int8/int4 already expanded to bf16) -> [out][3][in]
+int launch_conv_repack(const __nv_bfloat16* in, __nv_bfloat16* out, int c_out, int c_in, cudaStream_t stream);
+// mel f32 [B][T][m] -> bf16 [B][T+2][m] with zero rows 0 and T+1
+int launch_mel_pad_bf16(const float* mel, __nv_bfloat16* out, int B, int T, int m, cudaStream_t stream);
+int launch_fill_bf16_rows(__nv_bfloat16* base, long long batch_stride, int B, int row_elems, cudaStream_t stream);
+
+}  // namespace wb
