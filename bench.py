@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds per second for mel + encoder (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (torchrun launches it for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one pass of the hot path (log-mel of 30 s chunks + Whisper encoder forward) over one batch of synthetic
+chunks per GPU.  Workload at every N: whisper-large-v3 shape (128 mel, 32 layers, d = 1280), bf16 tensor-core math with
+fp32 accumulation / residual stream, 32 chunks per GPU per step (BASELINE.json configs[3]: 256 chunks over 8 GPUs), random-init
+weights serialised through the `.apr` v1 writer, synthetic audio.  Weak scaling: per-GPU work is fixed, chunks shard by
+batch, no data-path collective.
+
+`value`  : whole-job throughput with inputs resident in HBM (wb_mel_encode_batch_dev), CUDA events, max over ranks.
+`e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers (wb_mel_encode_batch): pinned host audio in,
+           pinned host encoder states out, copies inside the timed region.
+`roofline`: dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of its launches inside the step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec/sec, mel+encoder, whisper-large-v3 shape"
+UNIT = "audio-s/s"
+CHUNK_SECONDS = 30.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id: str):
+        self.rows, self.proc, self.gpu_id = [], None, gpu_id
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu_id, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(cfg_name: str, threads: int):
+    """Bounded sample of the reference's CPU algorithm (oracle/whisper_ref.c port) on one chunk of the bench workload; the
+    per-chunk time is extrapolated by exact op counts.  Returns (audio_s_per_s, description, seconds spent)."""
+    from oracle import cref
+    from oracle import encoder as E
+    from whisper_apr_b200 import synth
+    cfg = E.CONFIGS[cfg_name]
+    d, L, H, m = cfg.n_audio_state, cfg.n_audio_layer, cfg.n_audio_head, cfg.n_mels
+    rng = np.random.default_rng(0)
+    t_all = time.perf_counter()
+    audio = synth.synth_audio(0)
+    fb = synth.load_filterbank(m)
+    t0 = time.perf_counter(); mel = cref.compute_mel(audio, fb); t_mel = time.perf_counter() - t0
+    # conv stem on T_s of 3000 frames
+    T_s = 300 if d >= 768 else 3000
+    w = {"encoder.conv1.weight": (rng.standard_normal((d, m, 3)) / np.sqrt(3 * m)).astype(np.float32), "encoder.conv1.bias": np.zeros(d, np.float32),
+         "encoder.conv2.weight": (rng.standard_normal((d, d, 3)) / np.sqrt(3 * d)).astype(np.float32), "encoder.conv2.bias": np.zeros(d, np.float32)}
+    t0 = time.perf_counter(); x = cref.conv_stem(mel[:T_s], w, cfg); t_stem = (time.perf_counter() - t0) * (3000.0 / T_s)
+    # one encoder layer: attention (QKV/O via the vectorised matmul, all heads over `threads`) on all 1500 positions,
+    # scalar FFN on R of 1500 rows
+    lw = {}
+    p = "encoder.layers.0"
+    for k in ("q", "k", "v", "out"):
+        lw[f"{p}.self_attn.{k}_proj.weight"] = (rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
+    lw[f"{p}.fc1.weight"] = (rng.standard_normal((4 * d, d)) / np.sqrt(d)).astype(np.float32)
+    lw[f"{p}.fc2.weight"] = (rng.standard_normal((d, 4 * d)) / np.sqrt(4 * d)).astype(np.float32)
+    lw[f"{p}.fc1.bias"] = np.zeros(4 * d, np.float32); lw[f"{p}.fc2.bias"] = np.zeros(d, np.float32)
+    for n in ("self_attn_layer_norm", "final_layer_norm"):
+        lw[f"{p}.{n}.weight"] = np.ones(d, np.float32); lw[f"{p}.{n}.bias"] = np.zeros(d, np.float32)
+    W = cref.LayerWeights(lw, 0, d)
+    xs = rng.standard_normal((1500, d)).astype(np.float32)
+    t0 = time.perf_counter(); n1 = cref.layernorm(xs, W.ln1g, W.ln1b); t_ln = time.perf_counter() - t0
+    t0 = time.perf_counter(); cref.mha(n1, W, H, threads=threads); t_att = time.perf_counter() - t0
+    R = 1500 if d <= 384 else max(32, int(1500 * (384.0 / d) ** 2 / 4))
+    t0 = time.perf_counter(); cref.ffn(n1[:R], W); t_ffn = (time.perf_counter() - t0) * (1500.0 / R)
+    t_layer = 2 * t_ln + t_att + t_ffn
+    t_chunk = t_mel + t_stem + L * t_layer + t_ln
+    desc = (f"1 chunk of {cfg_name}: mel full; conv stem on {T_s}/3000 frames (x{3000 // T_s}); 1 of {L} layers with attention on all "
+            f"1500 positions ({threads} thread(s) over heads) and the scalar FFN on {R}/1500 rows, extrapolated by op count "
+            f"(mel {t_mel:.2f}s, stem {t_stem:.1f}s, layer {t_layer:.1f}s)")
+    return CHUNK_SECONDS / t_chunk, desc, time.perf_counter() - t_all
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    from oracle import cref
+    threads = cref.max_threads()
+    cref.lib()
+    vals, spent, desc = [], [], ""
+    for i in range(args.warmup + args.steps):
+        v, desc, s = cpu_sample(args.model, threads)
+        if i >= args.warmup:
+            vals.append(v); spent.append(s)
+        if sum(spent) > 240:
+            break
+    val = float(np.mean(vals))
+    chunks = args.chunks
+    out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+           "ms_per_step": 1e3 * chunks * CHUNK_SECONDS / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": workload_name(args), "chunks_per_gpu_per_step": chunks,
+                      "note": "reference = the reference's own CPU algorithm (C restatement oracle/whisper_ref.c; the Rust crate cannot be "
+                              "built offline), one process on the host cores; throughput does not grow with --gpus"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_name(args):
+    return {"large-v3": "whisper-large-v3 shape (128 mel, 32 enc layers, d=1280) bf16, 30 s chunks sharded by batch",
+            }.get(args.model, f"whisper-{args.model} shape bf16, 30 s chunks sharded by batch")
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--chunks", type=int, default=32, help="30 s chunks per GPU per step")
+    ap.add_argument("--quant", default="f32", choices=["f32", "int8", "int4"], help=".apr payload type (compute is bf16)")
+    ap.add_argument("--out-dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3                      # timing rule: >= 3 warm-up steps
+
+    import torch
+    import torch.distributed as dist
+    import whisper_apr_b200
+    from whisper_apr_b200 import WhisperApr, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = synth.CONFIGS[args.model]
+    B, d, S, m, L = args.chunks, cfg.n_audio_state, 1500, cfg.n_mels, cfg.n_audio_layer
+    quant = {"f32": 0, "int8": 2, "int4": 3}[args.quant]
+    t0 = time.time()
+    data, _ = synth.random_model_apr(cfg, quant=quant, seed=0)
+    model = WhisperApr.load_from_apr(data, device=local_rank)
+    del data
+    model.set_max_batch(B)
+    stream = torch.cuda.current_stream()
+    model.set_stream(stream.cuda_stream)
+    lib = whisper_apr_b200.lib()
+    setup_s = time.time() - t0
+
+    # inputs: ROT distinct batches so consecutive steps never re-read a hot L2 line
+    ROT = 3
+    host_audio = [torch.empty((B, synth.N_SAMPLES_30S), dtype=torch.float32).pin_memory() for _ in range(ROT)]
+    for r in range(ROT):
+        for i in range(B):
+            base = synth.synth_audio((rank * ROT + r) * B + i) if i < 4 else None
+            # 4 fully synthesised chunks per buffer, the rest are amplitude-scaled rolls of them (cheap, still distinct data)
+            host_audio[r][i] = torch.from_numpy(base) if base is not None else torch.roll(host_audio[r][i % 4], 1000 * i) * (0.5 + 0.01 * i)
+    dev_audio = [h.cuda(non_blocking=True) for h in host_audio]
+    out_t = torch.float32 if args.out_dtype == "f32" else torch.bfloat16
+    dev_out = torch.empty((B, S, d), dtype=out_t, device="cuda")
+    host_out = torch.empty((B, S, d), dtype=out_t).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_dev(i):
+        model.mel_encode_batch_dev(dev_audio[i % ROT].data_ptr(), B, dev_out.data_ptr(), args.out_dtype)
+
+    ptr_arrays = []
+    for r in range(ROT):
+        base = host_audio[r].data_ptr()
+        ptr_arrays.append(((C.c_void_p * B)(*[base + i * synth.N_SAMPLES_30S * 4 for i in range(B)]), (C.c_size_t * B)(*[synth.N_SAMPLES_30S] * B)))
+    code = 0 if args.out_dtype == "f32" else 1
+
+    def step_e2e(i):
+        ptrs, lens = ptr_arrays[i % ROT]
+        whisper_apr_b200._lib.check(lib.wb_mel_encode_batch(model._h, ptrs, lens, B, C.c_void_p(host_out.data_ptr()), code))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step_dev(i)
+    gpu_id = str(torch.cuda.get_device_properties(local_rank).uuid)
+    sampler = ClockSampler(gpu_id if gpu_id.startswith("GPU-") else "GPU-" + gpu_id)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.wb_launch_count()
+    ms = timed(step_dev, args.steps)
+    launches = lib.wb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    value = world * B * CHUNK_SECONDS * args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        for i in range(2):
+            step_e2e(i)
+        ms_e = timed(step_e2e, args.steps)
+        esz = 4 if args.out_dtype == "f32" else 2
+        e2e = {"value": world * B * CHUNK_SECONDS * args.steps / (ms_e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": B * synth.N_SAMPLES_30S * 4, "d2h_bytes_per_step": B * S * d * esz, "ms_per_step": ms_e / args.steps}
+
+    # per-kernel timing (CUDA events on the launching stream) over two more steps of the same region
+    peaks = load_peaks()
+    model.profile_enable(True)
+    PSTEPS = 2
+    for i in range(PSTEPS):
+        step_dev(i)
+    prof = model.profile_read()
+    model.profile_enable(False)
+    gemm_flops = B * (2 * 3000 * 3 * m * d + 2 * 1500 * 3 * d * d + L * 24 * S * d * d)
+    attn_flops = B * L * 4 * S * S * d
+    mel_bytes = B * (4 * synth.N_SAMPLES_30S + 2 * 3000 * m)
+    ln_bytes = B * S * d * ((2 * L) * 6 + 8)
+    g_ms = prof["gemm"]["ms"] / PSTEPS
+    a_ms = prof["attention"]["ms"] / PSTEPS
+    mel_ms = (prof["mel_stft"]["ms"] + prof["mel_finalize"]["ms"]) / PSTEPS
+    ln_ms = prof["layernorm"]["ms"] / PSTEPS
+    step_ms = ms / args.steps
+    roofline = {"kernel": "gemm_tn_kernel (tcgen05)", "bound": "tensor", "achieved": gemm_flops / (g_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": gemm_flops / (g_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": prof["gemm"]["launches"] // PSTEPS, "ms_per_step": g_ms, "share_of_step": g_ms / step_ms}
+    kernels = {
+        "attention": {"bound": "tensor", "achieved": attn_flops / (a_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "frac": attn_flops / (a_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                      "ms_per_step": a_ms, "share_of_step": a_ms / step_ms},
+        "mel": {"bound": "hbm", "achieved": mel_bytes / (mel_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": mel_bytes / (mel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "ms_per_step": mel_ms, "share_of_step": mel_ms / step_ms, "bytes": "f32 audio in + bf16 mel out"},
+        "layernorm": {"bound": "hbm", "achieved": ln_bytes / (ln_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": ln_bytes / (ln_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "ms_per_step": ln_ms, "share_of_step": ln_ms / step_ms},
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, desc, _ = cpu_sample(args.model, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+        except Exception as e:      # the CPU baseline must never take the GPU number down with it
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+               "data": "synthetic",
+               "config": {"workload": workload_name(args), "chunks_per_gpu_per_step": B, "global_chunks_per_step": world * B,
+                          "apr_payload": args.quant, "out_dtype": args.out_dtype,
+                          "l2": f"inputs rotate over {ROT} distinct batches ({ROT * B * 1.92:.0f} MB) and each step streams ~2 GB of activations, both > 126 MB L2",
+                          "parallelism": f"dp{world} (chunks sharded by batch, replicated weights, no data-path collective)",
+                          "setup_s": round(setup_s, 1)},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+               "cpu_baseline": cpu}
+        print(json.dumps(out), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,11 @@ int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_
 /* Encoder::forward_mel truncated after n_layers blocks (n_layers < 0: all), with or without ln_post: stage-wise parity. */
 int wb_debug_encode(const wb_model* m, const float* mel, size_t mel_len, int n_layers, int ln_post, float* out,
                     size_t out_capacity);
+/* Per-kernel timing for bench.py's roofline: while enabled, every launch of the model's path is bracketed by CUDA events on
+ * the launching stream; wb_profile_read synchronises and returns the summed milliseconds / launch counts per category
+ * {0 mel_stft, 1 mel_finalize, 2 gemm, 3 attention, 4 layernorm, 5 other} and clears the record. */
+int wb_profile_enable(wb_model* m, int on);
+int wb_profile_read(wb_model* m, float* ms_by_cat, int* launches_by_cat, int n_cat);
 /* Number of CUDA kernels this library has launched in this process (all models). */
 long long wb_launch_count(void);
 /* LayerNorm rows: x f32 [rows][d] -> out f32 (exact f32 result) */

@@ -208,6 +208,19 @@ class WhisperApr:
         check(_lib.lib().wb_encode_batch_dev(self._h, C.c_void_p(d_mel_ptr), B, C.c_void_p(d_out_ptr),
                                               WB_F32 if out_dtype == "f32" else WB_BF16))
 
+    # -- per-kernel timing (CUDA events on the launching stream) --------------------------
+    PROFILE_CATEGORIES = ("mel_stft", "mel_finalize", "gemm", "attention", "layernorm", "other")
+
+    def profile_enable(self, on: bool = True):
+        check(_lib.lib().wb_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        n = len(self.PROFILE_CATEGORIES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        check(_lib.lib().wb_profile_read(self._h, ms, cnt, n))
+        return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
     # -- test hook ---------------------------------------------------------------------
     def debug_encode(self, mel, n_layers: int = -1, ln_post: bool = True) -> np.ndarray:
         mel = _f32(mel).ravel()

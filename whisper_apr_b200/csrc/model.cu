@@ -92,6 +92,10 @@ struct wb_model {
   std::vector<wb::LayerW> layers;
   float *lnp_g = nullptr, *lnp_b = nullptr;
   wb::Workspace ws;
+  // per-kernel timing (wb_profile_*): CUDA events recorded on the launching stream around every launch
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;      // start/stop pairs
+  std::vector<int> prof_cat;
 };
 
 namespace wb {
@@ -107,6 +111,30 @@ struct DeviceGuard {
     if (ok) cudaSetDevice(prev);
   }
 };
+
+enum ProfCat { PC_MEL_STFT = 0, PC_MEL_FINALIZE = 1, PC_GEMM = 2, PC_ATTENTION = 3, PC_LAYERNORM = 4, PC_OTHER = 5, PC_COUNT = 6 };
+struct ProfScope {
+  wb_model* m;
+  cudaEvent_t stop = nullptr;
+  ProfScope(wb_model* model, int cat) : m(model) {
+    if (!m->prof_on) return;
+    cudaEvent_t start;
+    if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) { stop = nullptr; return; }
+    cudaEventRecord(start, m->stream);
+    m->prof_ev.push_back(start);
+    m->prof_ev.push_back(stop);
+    m->prof_cat.push_back(cat);
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, m->stream);
+  }
+};
+#define WB_PROF(cat, expr)      \
+  do {                          \
+    ProfScope _ps(m, cat);      \
+    rc = (expr);                \
+  } while (0);                  \
+  if (rc != WB_OK) return rc
 
 template <typename T>
 int dev_alloc(wb_model* m, size_t count, T** out) {
@@ -353,9 +381,8 @@ int encode_device(wb_model* m, int B, int T, void* d_out, wb_dtype out_dtype, in
   const int L = n_layers < 0 ? static_cast<int>(m->layers.size()) : std::min<int>(n_layers, static_cast<int>(m->layers.size()));
 
   // c1 guard rows (0 and T+1) are zero: conv2's padding
-  if ((rc = launch_fill_bf16_rows(w.c1.p, static_cast<long long>(T + 2) * d, B, d, st)) != WB_OK) return rc;
-  if ((rc = launch_fill_bf16_rows(w.c1.p + static_cast<long long>(T + 1) * d, static_cast<long long>(T + 2) * d, B, d, st)) != WB_OK)
-    return rc;
+  WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.c1.p, static_cast<long long>(T + 2) * d, B, d, st));
+  WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.c1.p + static_cast<long long>(T + 1) * d, static_cast<long long>(T + 2) * d, B, d, st));
 
   GemmDesc g{};
   // conv1 + GELU: row t of the operand = padded frames t, t+1, t+2 (3*nm contiguous values)
@@ -364,14 +391,14 @@ int encode_device(wb_model* m, int B, int T, void* d_out, wb_dtype out_dtype, in
   g.W = m->conv1_w; g.N = d; g.K = 3 * nm;
   g.epilogue = EPI_GELU_BF16; g.alpha = m->conv1_s; g.col_scale = nullptr; g.bias = m->conv1_b;
   g.out = w.c1.p; g.ldc = d; g.out_rows_per_batch = T + 2; g.out_row_off = 1; g.pe = nullptr;
-  if ((rc = launch_gemm(g, st)) != WB_OK) return rc;
+  WB_PROF(PC_GEMM, launch_gemm(g, st));
   // conv2 (stride 2) + GELU + positional embedding -> fp32 residual stream
   g.A = w.c1.p; g.a_row_stride = 2LL * d; g.a_batch_stride = static_cast<long long>(T + 2) * d;
   g.rows_per_batch = S; g.n_batch = B;
   g.W = m->conv2_w; g.N = d; g.K = 3 * d;
   g.epilogue = EPI_GELU_PE_F32; g.alpha = m->conv2_s; g.bias = m->conv2_b;
   g.out = w.x.p; g.ldc = d; g.out_rows_per_batch = S; g.out_row_off = 0; g.pe = m->pe;
-  if ((rc = launch_gemm(g, st)) != WB_OK) return rc;
+  WB_PROF(PC_GEMM, launch_gemm(g, st));
 
   const int M = B * S;
   auto flat = [&](const bf16* A, int K, const bf16* W, int N, int epi, float alpha, const float* cs, const float* bias, void* out) {
@@ -383,18 +410,17 @@ int encode_device(wb_model* m, int B, int T, void* d_out, wb_dtype out_dtype, in
   };
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = m->layers[i];
-    if ((rc = launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, nullptr, st)) != WB_OK) return rc;
-    if ((rc = flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p)) != WB_OK) return rc;
-    if ((rc = launch_attention(w.qkv.p, w.att.p, B, S, d, H, st)) != WB_OK) return rc;
-    if ((rc = flat(w.att.p, d, lw.wo, d, EPI_RESID_F32, lw.so, nullptr, lw.bo, w.x.p)) != WB_OK) return rc;
-    if ((rc = launch_layernorm(w.x.p, lw.ln2_g, lw.ln2_b, M, d, w.xn.p, nullptr, st)) != WB_OK) return rc;
-    if ((rc = flat(w.xn.p, d, lw.w1, 4 * d, EPI_GELU_BF16, lw.s1, nullptr, lw.b1, w.hid.p)) != WB_OK) return rc;
-    if ((rc = flat(w.hid.p, 4 * d, lw.w2, d, EPI_RESID_F32, lw.s2, nullptr, lw.b2, w.x.p)) != WB_OK) return rc;
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, nullptr, st));
+    WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p));
+    WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st));
+    WB_PROF(PC_GEMM, flat(w.att.p, d, lw.wo, d, EPI_RESID_F32, lw.so, nullptr, lw.bo, w.x.p));
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln2_g, lw.ln2_b, M, d, w.xn.p, nullptr, st));
+    WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.w1, 4 * d, EPI_GELU_BF16, lw.s1, nullptr, lw.b1, w.hid.p));
+    WB_PROF(PC_GEMM, flat(w.hid.p, 4 * d, lw.w2, d, EPI_RESID_F32, lw.s2, nullptr, lw.b2, w.x.p));
   }
   if (ln_post) {
-    if (out_dtype == WB_BF16) rc = launch_layernorm(w.x.p, m->lnp_g, m->lnp_b, M, d, static_cast<bf16*>(d_out), nullptr, st);
-    else rc = launch_layernorm(w.x.p, m->lnp_g, m->lnp_b, M, d, nullptr, static_cast<float*>(d_out), st);
-    if (rc != WB_OK) return rc;
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, m->lnp_g, m->lnp_b, M, d, out_dtype == WB_BF16 ? static_cast<bf16*>(d_out) : nullptr,
+                                           out_dtype == WB_BF16 ? nullptr : static_cast<float*>(d_out), st));
   } else {
     if (out_dtype == WB_BF16) rc = launch_f32_to_bf16(w.x.p, static_cast<bf16*>(d_out), static_cast<size_t>(M) * d, st);
     else {
@@ -411,17 +437,17 @@ int mel_device(wb_model* m, const float* d_audio, const int* d_n_valid, int B, f
   Workspace& w = m->ws;
   const int nm = m->mel.n_mels;
   const int n_frames = (N_SAMPLES_30S - N_FFT) / HOP + 1;     // 2998 (mel.rs:245-249)
-  int rc = launch_mel_stft(d_audio, N_SAMPLES_30S, d_n_valid, N_SAMPLES_30S, HOP, n_frames, B, m->mel, w.logmel.p, w.max_key.p,
-                           m->stream);
-  if (rc != WB_OK) return rc;
+  int rc;
+  WB_PROF(PC_MEL_STFT, launch_mel_stft(d_audio, N_SAMPLES_30S, d_n_valid, N_SAMPLES_30S, HOP, n_frames, B, m->mel, w.logmel.p,
+                                       w.max_key.p, m->stream));
   if (want_bf16) {
     const long long bs = static_cast<long long>(N_FRAMES_30S + 2) * nm;
-    if ((rc = launch_fill_bf16_rows(w.mel_bf16.p, bs, B, nm, m->stream)) != WB_OK) return rc;
-    if ((rc = launch_fill_bf16_rows(w.mel_bf16.p + static_cast<long long>(N_FRAMES_30S + 1) * nm, bs, B, nm, m->stream)) != WB_OK)
-      return rc;
+    WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.mel_bf16.p, bs, B, nm, m->stream));
+    WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.mel_bf16.p + static_cast<long long>(N_FRAMES_30S + 1) * nm, bs, B, nm, m->stream));
   }
-  return launch_mel_finalize(w.logmel.p, w.max_key.p, n_frames, N_FRAMES_30S, nm, B, d_mel_f32, want_bf16 ? w.mel_bf16.p : nullptr,
-                             m->stream);
+  WB_PROF(PC_MEL_FINALIZE, launch_mel_finalize(w.logmel.p, w.max_key.p, n_frames, N_FRAMES_30S, nm, B, d_mel_f32,
+                                               want_bf16 ? w.mel_bf16.p : nullptr, m->stream));
+  return WB_OK;
 }
 
 int check_encoder_dims(const wb_model* m) {
@@ -887,6 +913,31 @@ int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_
 }
 
 long long wb_launch_count(void) { return wb::g_launch_count.load(); }
+
+int wb_profile_enable(wb_model* m, int on) {
+  if (!m) return set_error(WB_ERR_MODEL, "null model");
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->prof_on = on != 0;
+  return WB_OK;
+}
+
+int wb_profile_read(wb_model* m, float* ms_by_cat, int* launches_by_cat, int n_cat) {
+  if (!m || !ms_by_cat || !launches_by_cat) return set_error(WB_ERR_MODEL, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  DeviceGuard guard(m->device);
+  WB_CUDA_OK(cudaStreamSynchronize(m->stream));
+  for (int i = 0; i < n_cat; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
+  for (size_t i = 0; i < m->prof_cat.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]);
+    const int c = m->prof_cat[i];
+    if (c < n_cat) { ms_by_cat[c] += ms; launches_by_cat[c] += 1; }
+  }
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  m->prof_ev.clear();
+  m->prof_cat.clear();
+  return WB_OK;
+}
 
 int wb_debug_encode(const wb_model* cm, const float* mel, size_t mel_len, int n_layers, int ln_post, float* out, size_t out_capacity) {
   wb_model* m = const_cast<wb_model*>(cm);
