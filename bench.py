@@ -206,7 +206,8 @@ def main():
     model = WhisperApr.load_from_apr(data, device=local_rank)
     del data
     model.set_max_batch(B)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()             # a real (non-legacy) stream: the kernels, copies and timing events all go here
+    torch.cuda.set_stream(stream)
     model.set_stream(stream.cuda_stream)
     lib = whisper_apr_b200.lib()
     setup_s = time.time() - t0

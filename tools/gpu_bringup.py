@@ -182,7 +182,22 @@ def case_quant():
         stats(f"encoder output tiny {nm} apr", model.encode(mel), ref)
 
 
-CASES = {"layernorm": case_layernorm, "gemm": case_gemm, "attention": case_attention, "mel": case_mel,
+def case_attn_perf():
+    """A full-size attention launch (8 chunks x 20 heads x 1500) for ncu: `ncu -k regex:attention ... --run attn_perf`."""
+    from whisper_apr_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    B, S, H = 8, 1500, 20
+    d = 64 * H
+    qkv = rng.standard_normal((B, S, 3 * d)).astype(np.float32)
+    out = np.empty((B, S, d), np.float32)
+    for _ in range(3):
+        t0 = time.time()
+        _lib.check(L.wb_debug_attention(0, _p(qkv), B, S, d, H, _p(out)))
+        print(f"  attn_perf call {time.time() - t0:.3f}s", flush=True)
+
+
+CASES = {"attn_perf": case_attn_perf, "layernorm": case_layernorm, "gemm": case_gemm, "attention": case_attention, "mel": case_mel,
          "encoder": case_encoder, "quant": case_quant}
 
 if __name__ == "__main__":
