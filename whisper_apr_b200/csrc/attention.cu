@@ -6,19 +6,26 @@
 // (running max / running sum) recurrence, just over KV blocks of 64 instead of 32 -- block size does not
 // change the result (the reference asserts this itself, attention.rs:2186-2228).  The encoder passes no mask.
 //
-// Warp-specialised kernel, one CTA = one (chunk, head, pair of 128-query tiles), 320 threads:
-//   warp 0      TMA producer: Q0/Q1 once, then a 4-stage ring of K_j / V_j tiles ([64][64] bf16, 128 B swizzle)
-//   warp 1      tcgen05.mma issuer.  Per KV block j (64 keys) and query tile t in {0,1}:
-//                 S_t[j&1] = Q_t K_j^T   4 x (128x64x16), both operands K-major            -> TMEM, double buffered
-//                 O_t     += P_t[j&1] V_j 4 x (128x64x16), A = P (smem), B = V_j MN-major   -> TMEM
-//               S_{j+1} is issued before the softmax of block j has finished, so the softmax warps never wait
-//               for the tensor core in steady state.
-//   warps 2-5   softmax warpgroup of tile 0, warps 6-9 of tile 1: thread r owns query row r == TMEM lane r.
+// Persistent warp-specialised kernel: one CTA per SM loops over work items (chunk, head, pair of 128-query tiles); 384 threads:
+//   warp 0      TMA producer: Q0/Q1 of the item (double buffered across items), then a 4-stage ring of K_j / V_j tiles
+//               ([64][64] bf16, 128 B swizzle); runs ahead of the consumers, also across item boundaries.
+//   warp 1      tcgen05.mma issuer of S_t[g&1] = Q_t K_j^T for both query tiles t: 4 x (128x64x16) each, both operands
+//               K-major, accumulators double buffered in TMEM, so S of the next block is ready before the softmax of the
+//               current block has finished.
+//   warps 2,3   tcgen05.mma issuers of O_t += P_t[g&1] V_j (one warp per tile): 4 x (128x64x16), A = P (smem),
+//               B = V_j used MN-major straight from its TMA tile.  (One issuing thread for everything was the
+//               bottleneck: ~20 dependent instructions per MMA on a single thread.)
+//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: thread r owns query row r == TMEM lane r.
 //               One tcgen05.ld pass keeps the 64 scores of the row in registers; running max with LAZY rescaling
 //               (O_t in TMEM is rescaled only when the max grows by more than 2^8, a rare TMEM read-modify-write);
 //               p = exp2(s*c - m*c) -> bf16 -> K-major swizzled P_t tile (double buffered) in shared memory.
-// TMEM columns: S_t[b] at t*128 + b*64 (256 total), O_t at 256 + t*64.   smem: Q 32 KB + K/V ring 64 KB + P 64 KB.
+//               The exponential phase is MUFU-bound; the two warpgroups pass a token through named barriers so their
+//               MUFU phases alternate while the other warpgroup does its barrier waits, tcgen05.ld and row max.
+// TMEM columns: S_t[b] at t*128 + b*64 (256 total), O_t at 256 + t*64.   smem: Q 64 KB + K/V ring 64 KB + P 64 KB.
 // The kernel is MUFU(ex2)-bound by construction: 2 x 8192 exponentials per (256 x 64) block at 16/clk/SM.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "wb_internal.h"
 
@@ -30,44 +37,57 @@ constexpr int Q_TILE_BYTES = BQ * DH * 2;          // 16 KB
 constexpr int KV_TILE_BYTES = BKV * DH * 2;        // 8 KB
 constexpr int P_TILE_BYTES = BQ * BKV * 2;         // 16 KB
 constexpr int KV_STAGES = 4;
-constexpr int WS_THREADS = 320;
-constexpr int WS_SMEM = 2 * Q_TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 4 * P_TILE_BYTES + 256;
+constexpr int WS_THREADS = 384;
+constexpr int WS_SMEM = 4 * Q_TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 4 * P_TILE_BYTES + 256;
 constexpr int WS_TMEM_COLS = 512;
 
 struct AttnParams {
   int S, d, n_kv_blocks;
+  int n_qpairs, n_heads, n_items;     // work items = B * n_heads * n_qpairs, q-pair fastest (neighbours share K/V through L2)
   float scale_log2;
   __nv_bfloat16* out;
+  long long* dbg;
 };
+
+#define ATT_PROBE(i)                                                                                   \
+  do {                                                                                                 \
+    if (p.dbg && blockIdx.x == 5 && threadIdx.x == 128 && it == 1 && j == 10) p.dbg[i] = clock64();     \
+  } while (0)
+
+__device__ __forceinline__ void item_coords(const AttnParams& p, int item, int& q0, int& h, int& b) {
+  const int qp = item % p.n_qpairs;
+  const int r = item / p.n_qpairs;
+  h = r % p.n_heads;
+  b = r / p.n_heads;
+  q0 = qp * 2 * BQ;
+}
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
 attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem;                                   // [2]
-  uint8_t* sK = smem + 2 * Q_TILE_BYTES;                // [KV_STAGES]
+  uint8_t* sQ = smem;                                   // [qbuf][tile]
+  uint8_t* sK = smem + 4 * Q_TILE_BYTES;                // [KV_STAGES]
   uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES]
   uint8_t* sP = sV + KV_STAGES * KV_TILE_BYTES;         // [tile][buf]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * P_TILE_BYTES);
-  uint64_t* q_full = bars;                              // 1
-  uint64_t* kv_full = bars + 1;                         // [4]
-  uint64_t* kv_empty = bars + 5;                        // [4]
-  uint64_t* s_full = bars + 9;                          // [tile*2 + buf]
-  uint64_t* p_full = bars + 13;                         // [tile*2 + buf], 128 arrivals
-  uint64_t* pv_done = bars + 17;                        // [tile*2 + buf]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* q_full = bars;                              // [2]
+  uint64_t* q_empty = bars + 2;                         // [2]
+  uint64_t* kv_full = bars + 4;                         // [4]
+  uint64_t* kv_empty = bars + 8;                        // [4]
+  uint64_t* s_full = bars + 12;                         // [tile*2 + buf]
+  uint64_t* p_full = bars + 16;                         // [tile*2 + buf], 4 arrivals (one per warp)
+  uint64_t* pv_done = bars + 20;                        // [tile*2 + buf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * BQ;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
   const int n = p.n_kv_blocks;
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 3); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
@@ -84,60 +104,80 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
-      mbar_expect_tx(q_full, 2 * Q_TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * DH, q0, b);
-      tma_load_3d(sQ + Q_TILE_BYTES, &tmQ, q_full, h * DH, q0 + BQ, b);
-      for (int j = 0; j < n; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t use = static_cast<uint32_t>(j / KV_STAGES);
-        mbar_wait(&kv_empty[st], (use & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full[st], 2 * KV_TILE_BYTES);
-        tma_load_3d(sK + st * KV_TILE_BYTES, &tmKV, &kv_full[st], p.d + h * DH, j * BKV, b);
-        tma_load_3d(sV + st * KV_TILE_BYTES, &tmKV, &kv_full[st], 2 * p.d + h * DH, j * BKV, b);
+      uint32_t g = 0;                                   // running KV block counter across items
+      int it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        int q0, h, b;
+        item_coords(p, item, q0, h, b);
+        const int qb = it & 1;
+        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], 2 * Q_TILE_BYTES);
+        tma_load_3d(sQ + (qb * 2) * Q_TILE_BYTES, &tmQ, &q_full[qb], h * DH, q0, b);
+        tma_load_3d(sQ + (qb * 2 + 1) * Q_TILE_BYTES, &tmQ, &q_full[qb], h * DH, q0 + BQ, b);
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t st = g % KV_STAGES;
+          mbar_wait(&kv_empty[st], ((g / KV_STAGES) & 1u) ^ 1u);
+          mbar_expect_tx(&kv_full[st], 2 * KV_TILE_BYTES);
+          tma_load_3d(sK + st * KV_TILE_BYTES, &tmKV, &kv_full[st], p.d + h * DH, j * BKV, b);
+          tma_load_3d(sV + st * KV_TILE_BYTES, &tmKV, &kv_full[st], 2 * p.d + h * DH, j * BKV, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
+      // ------------------------------------------------------------------ S = Q K^T issuer (both tiles)
       constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0);
+      uint32_t g = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int qb = it & 1;
+        mbar_wait(&q_full[qb], (it >> 1) & 1);
+        const uint64_t qd0 = umma_desc_sw128(smem_u32(sQ + (qb * 2) * Q_TILE_BYTES));
+        const uint64_t qd1 = umma_desc_sw128(smem_u32(sQ + (qb * 2 + 1) * Q_TILE_BYTES));
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t st = g % KV_STAGES, buf = g & 1u;
+          mbar_wait(&kv_full[st], (g / KV_STAGES) & 1u);
+          if (g >= 2) {                                      // S_t[buf] was consumed by the softmax of block g-2
+            mbar_wait(&p_full[buf], ((g - 2) >> 1) & 1u);
+            mbar_wait(&p_full[2 + buf], ((g - 2) >> 1) & 1u);
+          }
+          tc_fence_after_sync();
+          const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * KV_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + buf * 64, qd0 + 2 * k, kd + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[buf]);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + 128 + buf * 64, qd1 + 2 * k, kd + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[2 + buf]);
+          umma_commit(&kv_empty[st]);
+        }
+        umma_commit(&q_empty[qb]);                           // every S MMA of this item has been issued
+      }
+    }
+  } else if (warp < 4) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ O_t += P_t V issuer, one warp per tile
       constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, 1);     // B = V tile, MN-major
-      auto issue_s = [&](int t, int jj) {
-        const int st = jj % KV_STAGES, buf = jj & 1;
-        const uint32_t qa = smem_u32(sQ + t * Q_TILE_BYTES), ka = smem_u32(sK + st * KV_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_f16(tmem_base + t * 128 + buf * 64, umma_desc_sw128(qa + k * 32), umma_desc_sw128(ka + k * 32), idesc_s, k != 0);
-        umma_commit(&s_full[t * 2 + buf]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after_sync();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      for (int j = 0; j < n; ++j) {
-        const int st = j % KV_STAGES, buf = j & 1;
-        if (j + 1 < n) {
-          // S buffer (j+1)&1 of both tiles was released by p_full of block j-1, waited for in the previous iteration
-          mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
+      const int t = warp - 2;
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t st = g % KV_STAGES, buf = g & 1u;
+          mbar_wait(&kv_full[st], (g / KV_STAGES) & 1u);
+          mbar_wait(&p_full[t * 2 + buf], (g >> 1) & 1u);    // P_t(g) is in smem
           tc_fence_after_sync();
-          issue_s(0, j + 1);
-          issue_s(1, j + 1);
-        }
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t * 2 + buf], (j >> 1) & 1);      // P_t(j) is in smem, S_t[buf] has been consumed
-          tc_fence_after_sync();
-          const uint32_t pa = smem_u32(sP + (t * 2 + buf) * P_TILE_BYTES), va = smem_u32(sV + st * KV_TILE_BYTES);
+          const uint64_t pd = umma_desc_sw128(smem_u32(sP + (t * 2 + buf) * P_TILE_BYTES));
+          const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * KV_TILE_BYTES));
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            umma_f16(tmem_base + 256 + t * 64, umma_desc_sw128(pa + k * 32), umma_desc_sw128(va + k * 16 * 128), idesc_o, (j | k) != 0);
+          for (int k = 0; k < BKV / 16; ++k) umma_f16(tmem_base + 256 + t * 64, pd + 2 * k, vd + 128 * k, idesc_o, (j | k) != 0);
           umma_commit(&pv_done[t * 2 + buf]);
+          umma_commit(&kv_empty[st]);
         }
-        umma_commit(&kv_empty[st]);     // all MMAs reading K_j / V_j were issued before this commit
       }
     }
   } else {
     // -------------------------------------------------------------------- softmax warpgroups
-    const int t = (warp - 2) >> 2;                        // query tile of this warpgroup
+    const int t = (warp - 4) >> 2;                        // query tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;                 // row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + t * 128 + lane_sel;
@@ -145,95 +185,122 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t p_row = smem_u32(sP + t * 2 * P_TILE_BYTES) + r * 128;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const float c = p.scale_log2;
-    float m_ref = -INFINITY, l_run = 0.f;
+    const int my_items = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const uint32_t total_blocks = static_cast<uint32_t>(my_items) * n;
+    if (t == 1) asm volatile("bar.arrive %0, 256;" ::"r"(1) : "memory");      // warpgroup 0 owns the first token
 
-    for (int j = 0; j < n; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&s_full[t * 2 + buf], (j >> 1) & 1);
-      tc_fence_after_sync();
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32b_x32(tS + buf * 64, s0);
-      tmem_ld_32x32b_x32(tS + buf * 64 + 32, s1);
-      tmem_ld_wait();
-      const int kv_valid = p.S - j * BKV;                 // >= 64 except in the last block
-      if (kv_valid < BKV) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= kv_valid) s0[i] = 0xff800000u;         // -inf
-          if (32 + i >= kv_valid) s1[i] = 0xff800000u;
-        }
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-      // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
-      const bool need = (mx - m_ref) * c > 8.0f;
-      float alpha = 1.0f;
-      if (need) {
-        alpha = fast_exp2((m_ref - mx) * c);              // 0 on the first block (m_ref = -inf)
-        m_ref = mx;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        mbar_wait(&pv_done[t * 2 + (buf ^ 1)], ((j - 1) >> 1) & 1);       // PV_{j-1} retired: O_t is stable
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      int q0, h, b;
+      item_coords(p, item, q0, h, b);
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n; ++j, ++g) {
+        const uint32_t buf = g & 1u;
+        ATT_PROBE(0);
+        mbar_wait(&s_full[t * 2 + buf], (g >> 1) & 1u);
         tc_fence_after_sync();
+        ATT_PROBE(1);
+        uint32_t s0[32], s1[32];
+        tmem_ld_32x32b_x32(tS + buf * 64, s0);
+        tmem_ld_32x32b_x32(tS + buf * 64 + 32, s1);
+        // P_t[buf] is free once PV of block g-2 retired; probe early so the barrier latency hides behind the loads and the max
+        bool pv_ok = true;
+        if (g >= 2) pv_ok = mbar_try_wait(&pv_done[t * 2 + buf], ((g - 2) >> 1) & 1u);
+        tmem_ld_wait();
+        ATT_PROBE(2);
+        const int kv_valid = p.S - j * BKV;                 // >= 64 except in the last block
+        if (kv_valid < BKV) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tO + cc * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st_32x32b_x32(tO + cc * 32, v);
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_valid) s0[i] = 0xff800000u;         // -inf
+            if (32 + i >= kv_valid) s1[i] = 0xff800000u;
+          }
         }
-        tmem_st_wait();
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
+        const bool need = (mx - m_ref) * c > 8.0f;
+        float alpha = 1.0f;
+        if (need) {
+          alpha = fast_exp2((m_ref - mx) * c);              // 0 on the first block (m_ref = -inf)
+          m_ref = mx;
+        }
+        ATT_PROBE(3);
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[t * 2 + (buf ^ 1u)], ((g - 1) >> 1) & 1u);     // PV of the previous block retired: O_t is stable
+          tc_fence_after_sync();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tO + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(tO + cc * 32, v);
+          }
+          tmem_st_wait();
+        }
+        if (!pv_ok) mbar_wait(&pv_done[t * 2 + buf], ((g - 2) >> 1) & 1u);
+        ATT_PROBE(4);
+        const float mb = m_ref * c;
+        // ping-pong token: MUFU phases of the two warpgroups alternate
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        ATT_PROBE(5);
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t pb = p_row + buf * P_TILE_BYTES;
+        auto emit = [&](const uint32_t (&sv)[32], int cgrp) {
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = fast_exp2(__uint_as_float(sv[8 * gg + i]) * c - mb);   // exp2(-inf) == 0: masked
+            rs4[gg] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            const uint32_t chunk = static_cast<uint32_t>(cgrp * 4 + gg);
+            const uint32_t addr = pb + ((chunk ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
+                         "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
+                         : "memory");
+          }
+        };
+        emit(s0, 0);
+        emit(s1, 1);
+        if (!(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
+        ATT_PROBE(6);
+        l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+        fence_proxy_async_smem();                           // generic-proxy P writes -> visible to the tensor core (async proxy)
+        tc_fence_before_sync();
+        __syncwarp();
+        ATT_PROBE(7);
+        if (lane == 0) mbar_arrive(&p_full[t * 2 + buf]);
+        ATT_PROBE(8);
       }
-      if (j >= 2) mbar_wait(&pv_done[t * 2 + buf], ((j - 2) >> 1) & 1);    // PV_{j-2} retired: P_t[buf] is free
-      const float mb = m_ref * c;
-      float rs = 0.f;
-      const uint32_t pb = p_row + static_cast<uint32_t>(buf) * P_TILE_BYTES;
-      auto emit = [&](const uint32_t (&sv)[32], int cgrp) {
+      // epilogue: O_t / l  (attention.rs:334-343: 0 when the sum is <= 1e-10)
+      mbar_wait(&pv_done[t * 2 + ((g - 1) & 1u)], ((g - 1) >> 1) & 1u);
+      tc_fence_after_sync();
+      const int row = q0 + t * BQ + r;
+      const float inv = l_run > 1e-10f ? 1.0f / l_run : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.S + row) * p.d + h * DH);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float e[8];
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO + cc * 32, v);
+        tmem_ld_wait();
+        if (row < p.S) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = fast_exp2(__uint_as_float(sv[8 * g + i]) * c - mb);   // exp2(-inf) == 0: masked
-          rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-          const uint32_t chunk = static_cast<uint32_t>(cgrp * 4 + g);
-          const uint32_t addr = pb + ((chunk ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
-                       "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
-                       : "memory");
-        }
-      };
-      emit(s0, 0);
-      emit(s1, 1);
-      l_run = l_run * alpha + rs;
-      fence_proxy_async_smem();                           // generic-proxy P writes -> visible to the tensor core (async proxy)
-      tc_fence_before_sync();
-      mbar_arrive(&p_full[t * 2 + buf]);
-    }
-    // epilogue: O_t / l  (attention.rs:334-343: 0 when the sum is <= 1e-10)
-    mbar_wait(&pv_done[t * 2 + ((n - 1) & 1)], ((n - 1) >> 1) & 1);
-    tc_fence_after_sync();
-    const int row = q0 + t * BQ + r;
-    const float inv = l_run > 1e-10f ? 1.0f / l_run : 0.f;
-    uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.S + row) * p.d + h * DH);
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tO + cc * 32, v);
-      tmem_ld_wait();
-      if (row < p.S) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v[8 * g + 0]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
-          dst[cc * 4 + g] = w;
+          for (int gg = 0; gg < 4; ++gg) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * gg + 0]) * inv, __uint_as_float(v[8 * gg + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(v[8 * gg + 2]) * inv, __uint_as_float(v[8 * gg + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(v[8 * gg + 4]) * inv, __uint_as_float(v[8 * gg + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(v[8 * gg + 6]) * inv, __uint_as_float(v[8 * gg + 7]) * inv);
+            dst[cc * 4 + gg] = w;
+          }
         }
       }
+      tc_fence_before_sync();       // the next item's first PV (issued after this warpgroup's next p_full) overwrites O_t
     }
   }
   tc_fence_before_sync();
@@ -245,12 +312,16 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 bool g_att_init = false;
+int g_att_sms = 0;
 
 }  // namespace
 
 int attention_init() {
   if (g_att_init) return WB_OK;
   WB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+  int dev = 0;
+  WB_CUDA_OK(cudaGetDevice(&dev));
+  WB_CUDA_OK(cudaDeviceGetAttribute(&g_att_sms, cudaDevAttrMultiProcessorCount, dev));
   g_att_init = true;
   return WB_OK;
 }
@@ -269,12 +340,28 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S,
   p.S = S;
   p.d = d;
   p.n_kv_blocks = (S + BKV - 1) / BKV;
+  p.n_qpairs = (S + 2 * BQ - 1) / (2 * BQ);
+  p.n_heads = n_heads;
+  p.n_items = B * n_heads * p.n_qpairs;
   p.scale_log2 = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
   p.out = out;
-  dim3 grid((S + 2 * BQ - 1) / (2 * BQ), n_heads, B);
+  p.dbg = nullptr;
+  if (getenv("WB_ATTN_PROBE")) {
+    static long long* d_dbg = nullptr;
+    if (!d_dbg) cudaMalloc(&d_dbg, 16 * sizeof(long long));
+    p.dbg = d_dbg;
+  }
+  const int grid = p.n_items < g_att_sms ? p.n_items : g_att_sms;
   attention_ws_kernel<<<grid, WS_THREADS, WS_SMEM, stream>>>(tq, tkv, p);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
+  if (p.dbg) {
+    cudaStreamSynchronize(stream);
+    long long hh[16];
+    cudaMemcpy(hh, p.dbg, sizeof hh, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[attn probe] wait_s %lld ldtm %lld max %lld pvwait %lld token %lld exp %lld fence %lld arrive %lld | block %lld\n", hh[1] - hh[0],
+            hh[2] - hh[1], hh[3] - hh[2], hh[4] - hh[3], hh[5] - hh[4], hh[6] - hh[5], hh[7] - hh[6], hh[8] - hh[7], hh[8] - hh[0]);
+  }
   return WB_OK;
 }
 
