@@ -47,6 +47,7 @@ struct AttnParams {
   float scale_log2;
   __nv_bfloat16* out;
   long long* dbg;
+  int use_token;
 };
 
 #define ATT_PROBE(i)                                                                                   \
@@ -187,7 +188,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float c = p.scale_log2;
     const int my_items = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const uint32_t total_blocks = static_cast<uint32_t>(my_items) * n;
-    if (t == 1) asm volatile("bar.arrive %0, 256;" ::"r"(1) : "memory");      // warpgroup 0 owns the first token
+    if (p.use_token && t == 1) asm volatile("bar.arrive %0, 256;" ::"r"(1) : "memory");      // warpgroup 0 owns the first token
 
     uint32_t g = 0;
     int it = 0;
@@ -247,7 +248,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ATT_PROBE(4);
         const float mb = m_ref * c;
         // ping-pong token: MUFU phases of the two warpgroups alternate
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        if (p.use_token) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
         ATT_PROBE(5);
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
         const uint32_t pb = p_row + buf * P_TILE_BYTES;
@@ -267,7 +268,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         };
         emit(s0, 0);
         emit(s1, 1);
-        if (!(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
+        if (p.use_token && !(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
         ATT_PROBE(6);
         l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
         fence_proxy_async_smem();                           // generic-proxy P writes -> visible to the tensor core (async proxy)
@@ -346,6 +347,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S,
   p.scale_log2 = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
   p.out = out;
   p.dbg = nullptr;
+  p.use_token = getenv("WB_ATTN_NOTOKEN") ? 0 : 1;
   if (getenv("WB_ATTN_PROBE")) {
     static long long* d_dbg = nullptr;
     if (!d_dbg) cudaMalloc(&d_dbg, 16 * sizeof(long long));

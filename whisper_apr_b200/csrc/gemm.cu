@@ -18,6 +18,7 @@
 // contiguous values starting at padded frame t (row stride n_mels), and row p of the conv2 operand is the
 // 3*d values starting at padded position 2p (row stride 2d).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "wb_internal.h"
@@ -248,6 +249,150 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs (the two SMs of a TPC) computes one 256 x BN tile.  Each CTA stages
+// its own 128 rows of A and HALF of the W tile (BN/2 rows) per k-block, the leader CTA issues 256 x BN x 16 MMAs that read
+// both halves, and each CTA's TMEM receives its own 128 accumulator rows.  Per SM this halves the W traffic through shared
+// memory and L2 (the 1-CTA kernel needs 96 B/clk of operand reads plus 96 B/clk of TMA writes against a 128 B/clk shared-memory
+// port), which is what bounds the 1-CTA kernel at ~75 % of the cuBLAS rate.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's half of the W tile
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* full = bars;                       // used in the leader only (both CTAs' TMA bytes land here)
+  uint64_t* empty = bars + STAGES;             // per CTA, signalled by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * STAGES;         // per CTA, multicast commit
+  uint64_t* tempty = tfull + 2;                // leader only: 4 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();     // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                          // barriers of both CTAs are initialised before any remote arrive / multicast
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int tiles_m = (p.rows_per_batch + 2 * BM - 1) / (2 * BM);      // 256-row tiles per batch entry
+  const int num_tiles = p.n_batch * tiles_m * p.tiles_n;
+  const int kblocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int nb = tile % p.tiles_n;
+        const int mb = tile / p.tiles_n;
+        const int b = mb / tiles_m;
+        const int mt = mb - b * tiles_m;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+          tma_load_3d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, mt * 2 * BM + static_cast<int>(rank) * BM, b);
+          tma_load_3d_2sm(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BK, nb * BN + static_cast<int>(rank) * (BN / 2), 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+        const uint32_t buf = it & 1u;
+        const uint32_t use = it >> 1;
+        mbar_wait(&tempty[buf], (use & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[stage]);      // frees the stage in both CTAs once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tfull[buf]);           // accumulators ready for both CTAs' epilogues
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5 of both CTAs)
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+      const uint32_t buf = it & 1u;
+      const uint32_t use = it >> 1;
+      const int nb = tile % p.tiles_n;
+      const int mb = tile / p.tiles_n;
+      const int b = mb / tiles_m;
+      const int mt = mb - b * tiles_m;
+      const int r_in_batch = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
+      const bool row_ok = r_in_batch < p.rows_per_batch;
+      const long long out_row = static_cast<long long>(b) * p.out_rows_per_batch + p.out_row_off + r_in_batch;
+      mbar_wait(&tfull[buf], use & 1u);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        const int n0 = nb * BN + c * 32;
+        if (row_ok && n0 < p.N) epilogue_store<EPI>(p, v, out_row, r_in_batch, n0);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                          // neither CTA exits (or frees TMEM) while its peer may still touch it
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -266,6 +411,33 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKPara
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
+}
+
+template <int BN, int EPI>
+int launch_variant2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, int num_tiles2, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WB_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM));
+    attr_set = true;
+  }
+  int pairs = g_num_sms / 2;
+  if (num_tiles2 < pairs) pairs = num_tiles2;
+  gemm2_tn_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM, stream>>>(ta, tb, kp);
+  count_launch();
+  WB_CUDA_OK(cudaGetLastError());
+  return WB_OK;
+}
+
+template <int BN>
+int launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, int num_tiles2, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch_variant2<BN, EPI_BF16>(ta, tb, kp, num_tiles2, s);
+    case EPI_GELU_BF16: return launch_variant2<BN, EPI_GELU_BF16>(ta, tb, kp, num_tiles2, s);
+    case EPI_RESID_F32: return launch_variant2<BN, EPI_RESID_F32>(ta, tb, kp, num_tiles2, s);
+    case EPI_GELU_PE_F32: return launch_variant2<BN, EPI_GELU_PE_F32>(ta, tb, kp, num_tiles2, s);
+    case EPI_F32: return launch_variant2<BN, EPI_F32>(ta, tb, kp, num_tiles2, s);
+  }
+  return set_error(WB_ERR_MODEL, "unknown GEMM epilogue");
 }
 
 template <int BN>
@@ -328,7 +500,9 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   rc = make_tmap_bf16_3d(&ta, g.A, g.K, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.a_row_stride) * 2, batch_stride,
                          BK, BM);
   if (rc != WB_OK) return rc;
-  rc = make_tmap_bf16_3d(&tb, g.W, g.K, g.N, 1, static_cast<uint64_t>(g.K) * 2, static_cast<uint64_t>(g.K) * 2 * g.N, BK, BN);
+  static const bool one_cta = getenv("WB_GEMM_1CTA") != nullptr;       // bring-up / A-B switch: the CTA-pair kernel is the product path
+  rc = make_tmap_bf16_3d(&tb, g.W, g.K, g.N, 1, static_cast<uint64_t>(g.K) * 2, static_cast<uint64_t>(g.K) * 2 * g.N, BK,
+                         one_cta ? BN : BN / 2);
   if (rc != WB_OK) return rc;
   GemmKParams kp;
   kp.rows_per_batch = g.rows_per_batch;
@@ -345,6 +519,11 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.bias = g.bias;
   kp.out = g.out;
   kp.pe = g.pe;
+  if (!one_cta) {
+    const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
+    if (BN == 256) return launch_bn2<256>(g.epilogue, ta, tb, kp, num_tiles2, stream);
+    return launch_bn2<128>(g.epilogue, ta, tb, kp, num_tiles2, stream);
+  }
   const int num_tiles = kp.n_batch * kp.tiles_m_per_batch * kp.tiles_n;
   if (BN == 256) return launch_bn<256>(g.epilogue, ta, tb, kp, num_tiles, stream);
   return launch_bn<128>(g.epilogue, ta, tb, kp, num_tiles, stream);
