@@ -26,6 +26,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 #include "wb_internal.h"
 
@@ -196,7 +198,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int q0, h, b;
       item_coords(p, item, q0, h, b);
       float m_ref = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < n; ++j, ++g) {
+      // one KV block; `masked` selects the tail-block variant (keeps 128 compare/select instructions out of the common path)
+      auto block_body = [&](int j, auto masked) {
         const uint32_t buf = g & 1u;
         ATT_PROBE(0);
         mbar_wait(&s_full[t * 2 + buf], (g >> 1) & 1u);
@@ -211,7 +214,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_ld_wait();
         ATT_PROBE(2);
         const int kv_valid = p.S - j * BKV;                 // >= 64 except in the last block
-        if (kv_valid < BKV) {
+        if constexpr (decltype(masked)::value) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i >= kv_valid) s0[i] = 0xff800000u;         // -inf
@@ -277,6 +280,10 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ATT_PROBE(7);
         if (lane == 0) mbar_arrive(&p_full[t * 2 + buf]);
         ATT_PROBE(8);
+      };
+      for (int j = 0; j < n; ++j, ++g) {
+        if (p.S - j * BKV < BKV) block_body(j, std::true_type{});
+        else block_body(j, std::false_type{});
       }
       // epilogue: O_t / l  (attention.rs:334-343: 0 when the sum is <= 1e-10)
       mbar_wait(&pv_done[t * 2 + ((g - 1) & 1u)], ((g - 1) >> 1) & 1u);

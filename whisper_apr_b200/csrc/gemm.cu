@@ -309,27 +309,29 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer (both CTAs)
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-        const int nb = tile % p.tiles_n;
-        const int mb = tile / p.tiles_n;
-        const int b = mb / tiles_m;
-        const int mt = mb - b * tiles_m;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); lane 0 issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+      const int nb = tile % p.tiles_n;
+      const int mb = tile / p.tiles_n;
+      const int b = mb / tiles_m;
+      const int mt = mb - b * tiles_m;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (lane == 0) {
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
           tma_load_3d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, mt * 2 * BM + static_cast<int>(rank) * BM, b);
           tma_load_3d_2sm(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BK, nb * BN + static_cast<int>(rank) * (BN / 2), 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only; lane 0 issues)
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -345,12 +347,16 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after_sync();
           const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
           const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty[stage]);      // frees the stage in both CTAs once these MMAs retire
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[stage]);      // frees the stage in both CTAs once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_2sm(&tfull[buf]);           // accumulators ready for both CTAs' epilogues
+        if (lane == 0) umma_commit_2sm(&tfull[buf]);           // accumulators ready for both CTAs' epilogues
+        __syncwarp();
       }
     }
   } else {
