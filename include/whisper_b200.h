@@ -144,6 +144,9 @@ int wb_debug_gemm(int device, const float* A, const float* W, const float* bias,
                   int K, int epilogue, float alpha, float* out);
 /* One attention call: qkv f32 [B][S][3d] (rounded to bf16) -> out f32 [B][S][d]. */
 int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_heads, float* out);
+/* Times `iters` back-to-back attention launches on device-resident pseudo-random bf16 qkv [B][S][3d] (CUDA events on the
+ * launching stream, after 2 warm-up launches); *ms_per_launch receives the mean.  Kernel tuning only. */
+int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int iters, float* ms_per_launch);
 /* Encoder::forward_mel truncated after n_layers blocks (n_layers < 0: all), with or without ln_post: stage-wise parity. */
 int wb_debug_encode(const wb_model* m, const float* mel, size_t mel_len, int n_layers, int ln_post, float* out,
                     size_t out_capacity);

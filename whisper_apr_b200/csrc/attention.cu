@@ -335,6 +335,8 @@ int attention_init() {
 }
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream) {
+  static const bool old_kernel = getenv("WB_ATTN_OLD") != nullptr;      // A/B switch: attention_tm.cu is the product path
+  if (!old_kernel) return launch_attention_tm(qkv, out, B, S, d, n_heads, stream);
   int rc = attention_init();
   if (rc != WB_OK) return rc;
   if (B <= 0 || S <= 0) return WB_OK;

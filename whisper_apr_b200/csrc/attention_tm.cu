@@ -1,0 +1,399 @@
+// Non-causal multi-head self-attention on tcgen05 with the probabilities kept in TENSOR MEMORY.
+//
+// Same contract as attention.cu (MultiHeadAttention::forward_cross_flash, src/model/attention.rs:894-935, per head
+// flash_attention_simd, attention.rs:472-519: online softmax with running max / running sum, scale 1/sqrt(64), no mask);
+// the KV block is 128 keys instead of the reference's 32 -- the block size does not change the result
+// (attention.rs:2186-2228 asserts exactly that).
+//
+// Why a second kernel: the exponential (MUFU.EX2, 16/clk/SM) is the binding pipe for d_head = 64 -- 2x the tensor time --
+// so everything that is not an exponential has to hide behind one.  Per 64-key block the first kernel spent as long in
+// barrier / fence / shared-memory-staging latency as in the exponentials.  Here
+//   * the KV block is 128 keys: half as many synchronisation rounds per exponential;
+//   * P never touches shared memory: the softmax warps write bf16 P straight back to TMEM (tcgen05.st) and the PV MMA takes
+//     its A operand from TMEM -- no st.shared, no generic->async proxy fence;
+//   * a softmax thread holds its whole 128-score row in registers (setmaxnreg moves registers from the four single-thread
+//     role warps to the two softmax warpgroups), so S_t is released right after the tcgen05.ld and the next QK^T runs
+//     under the exponentials of the current block;
+//   * the two softmax warpgroups (one per 128-query tile) alternate their exponential phases through a named-barrier token,
+//     so while one is MUFU-bound the other does its waits, loads, row max and P store.
+//
+// One persistent CTA per SM, work item = (chunk, head, pair of 128-query tiles), 384 threads:
+//   warp 0      TMA producer: Q0/Q1 (double buffered across items), ring of K_j / V_j tiles ([128][64] bf16, 128 B swizzle)
+//   warp 1      S_t = Q_t K_j^T issuer (4 x 128x128x16 per tile)
+//   warps 2,3   O_t += P_t V_j issuers (8 x 128x64x16, A = P_t in TMEM, B = V_j MN-major from its TMA tile)
+//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1; thread r owns query row r == TMEM lane r
+// TMEM columns: S_t at t*128 (256), O_t at 256 + t*64 (128), P_t at 384 + t*64 (128; 128 keys x bf16 = 64 columns).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "ptx.cuh"
+#include "wb_internal.h"
+
+namespace wb {
+namespace {
+
+constexpr int BQ = 128, BKV = 128, DH = 64;
+constexpr int Q_TILE_BYTES = BQ * DH * 2;          // 16 KB
+constexpr int KV_TILE_BYTES = BKV * DH * 2;        // 16 KB
+constexpr int KV_STAGES = 4;
+constexpr int TM_THREADS = 384;
+constexpr int TM_SMEM = 4 * Q_TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 256;
+constexpr uint32_t TM_COLS = 512, COL_S = 0, COL_O = 256, COL_P = 384;
+constexpr int REGS_ROLE = 40, REGS_SOFTMAX = 232;   // 128*40 + 256*232 == 384*168
+
+struct AttnTmParams {
+  int S, d, n_kv_blocks;
+  int n_qpairs, n_heads, n_items;     // work items = B * n_heads * n_qpairs, q-pair fastest (neighbours share K/V through L2)
+  float scale_log2;
+  __nv_bfloat16* out;
+  int use_token;
+};
+
+__device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int& q0, int& h, int& b) {
+  const int qp = item % p.n_qpairs;
+  const int r = item / p.n_qpairs;
+  h = r % p.n_heads;
+  b = r / p.n_heads;
+  q0 = qp * 2 * BQ;
+}
+
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], relative error 1.1e-4 -- well
+// inside the bf16 rounding of P): keeps part of the exponentials off the MUFU pipe, which bounds this kernel.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                  // 1.5 * 2^23: low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);            // [-0.5, 0.5]
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// exponentials of one 128-score row -> packed bf16 pairs (what tcgen05.st writes as P) and the row sum.
+// The scale-and-shift runs as packed FFMA2, the exponentials are issued in batches of 16 and a batch is consumed (bf16 pack,
+// packed FADD2 row sum) only after the NEXT batch has been issued: a lone warp per scheduler otherwise stalls on every MUFU result.
+// Element i goes to the FMA-pipe polynomial when bit (i & 7) of kPolyMask is set -- a compile-time choice after unrolling.
+template <int kPolyMask>
+__device__ __forceinline__ float exp_row(uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb) {
+  const uint64_t c2 = pack_f32x2(c, c), nmb2 = pack_f32x2(-mb, -mb);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    float x0, x1;
+    unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c2, nmb2), x0, x1);
+    s[2 * i] = __float_as_uint(x0);
+    s[2 * i + 1] = __float_as_uint(x1);
+  }
+  uint64_t acc[2] = {0ull, 0ull};
+  auto consume = [&](int bt) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = bt * 8 + i;
+      const float e0 = __uint_as_float(s[2 * e]), e1 = __uint_as_float(s[2 * e + 1]);
+      acc[i & 1] = fadd2(acc[i & 1], pack_f32x2(e0, e1));
+      pk[e] = pack_bf16x2(e0, e1);
+    }
+  };
+#pragma unroll
+  for (int bt = 0; bt < 8; ++bt) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = bt * 16 + i;
+      const float x = __uint_as_float(s[e]);                 // exp2(-inf) == 0: masked keys contribute nothing
+      s[e] = __float_as_uint(((kPolyMask >> (e & 7)) & 1) ? poly_exp2(x) : fast_exp2(x));
+    }
+    if (bt > 0) consume(bt - 1);
+  }
+  consume(7);
+  float a0, a1, a2, a3;
+  unpack_f32x2(acc[0], a0, a1);
+  unpack_f32x2(acc[1], a2, a3);
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <int kPolyMask>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                                   // [qbuf][tile]
+  uint8_t* sK = smem + 4 * Q_TILE_BYTES;                // [KV_STAGES]
+  uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_TILE_BYTES);
+  uint64_t* q_full = bars;                              // [2]
+  uint64_t* q_empty = bars + 2;                         // [2]
+  uint64_t* k_full = bars + 4;                          // [KV_STAGES]
+  uint64_t* v_full = bars + 8;                          // [KV_STAGES]
+  uint64_t* kv_empty = bars + 12;                       // [KV_STAGES]  3 arrivals: S issuer + two PV issuers
+  uint64_t* s_full = bars + 16;                         // [tile]
+  uint64_t* s_free = bars + 18;                         // [tile]  4 arrivals (one per softmax warp): S_t is in registers
+  uint64_t* p_full = bars + 20;                         // [tile]  4 arrivals: P_t is in TMEM
+  uint64_t* pv_done = bars + 22;                        // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n = p.n_kv_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 3); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQKV);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp < 4) {
+    reg_dealloc<REGS_ROLE>();
+    if (warp == 0) {
+      if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        uint32_t g = 0;                                   // running KV block counter across items
+        int it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+          int q0, h, b;
+          item_coords(p, item, q0, h, b);
+          const int qb = it & 1;
+          mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[qb], 2 * Q_TILE_BYTES);
+          tma_load_3d(sQ + (qb * 2) * Q_TILE_BYTES, &tmQKV, &q_full[qb], h * DH, q0, b);
+          tma_load_3d(sQ + (qb * 2 + 1) * Q_TILE_BYTES, &tmQKV, &q_full[qb], h * DH, q0 + BQ, b);
+          for (int j = 0; j < n; ++j, ++g) {
+            const uint32_t st = g % KV_STAGES;
+            mbar_wait(&kv_empty[st], ((g / KV_STAGES) & 1u) ^ 1u);
+            mbar_expect_tx(&k_full[st], KV_TILE_BYTES);
+            tma_load_3d(sK + st * KV_TILE_BYTES, &tmQKV, &k_full[st], p.d + h * DH, j * BKV, b);
+            mbar_expect_tx(&v_full[st], KV_TILE_BYTES);
+            tma_load_3d(sV + st * KV_TILE_BYTES, &tmQKV, &v_full[st], 2 * p.d + h * DH, j * BKV, b);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ------------------------------------------------------------------ S_t = Q_t K^T issuer (both tiles)
+        constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0);
+        uint32_t g = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+          const int qb = it & 1;
+          mbar_wait(&q_full[qb], (it >> 1) & 1);
+          const uint64_t qd[2] = {umma_desc_sw128(smem_u32(sQ + (qb * 2) * Q_TILE_BYTES)),
+                                  umma_desc_sw128(smem_u32(sQ + (qb * 2 + 1) * Q_TILE_BYTES))};
+          for (int j = 0; j < n; ++j, ++g) {
+            const uint32_t st = g % KV_STAGES;
+            mbar_wait(&k_full[st], (g / KV_STAGES) & 1u);
+            const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * KV_TILE_BYTES));
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              if (g >= 1) mbar_wait(&s_free[t], (g - 1) & 1u);         // the softmax warpgroup holds S_t(g-1) in registers
+              tc_fence_after_sync();
+#pragma unroll
+              for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + COL_S + t * 128, qd[t] + 2 * k, kd + 2 * k, idesc_s, k != 0);
+              umma_commit(&s_full[t]);
+            }
+            umma_commit(&kv_empty[st]);
+          }
+          umma_commit(&q_empty[qb]);                                    // every S MMA of this item has been issued
+        }
+      }
+    } else {
+      if (lane == 0) {
+        // ------------------------------------------------------------------ O_t += P_t V issuer, one warp per tile
+        constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, 1);        // B = V tile, MN-major
+        const int t = warp - 2;
+        const uint32_t tO = tmem_base + COL_O + t * 64;
+        const uint32_t tP = tmem_base + COL_P + t * 64;
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          for (int j = 0; j < n; ++j, ++g) {
+            const uint32_t st = g % KV_STAGES;
+            mbar_wait(&v_full[st], (g / KV_STAGES) & 1u);
+            mbar_wait(&p_full[t], g & 1u);                              // P_t(g) is in TMEM
+            tc_fence_after_sync();
+            const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * KV_TILE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k) umma_f16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_o, (j | k) != 0);
+            umma_commit(&pv_done[t]);
+            umma_commit(&kv_empty[st]);
+          }
+        }
+      }
+    }
+  } else {
+    reg_alloc<REGS_SOFTMAX>();
+    // -------------------------------------------------------------------- softmax warpgroups
+    const int t = (warp - 4) >> 2;                        // query tile of this warpgroup
+    const int r = (warp & 3) * 32 + lane;                 // row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + COL_S + t * 128 + lane_sel;
+    const uint32_t tO = tmem_base + COL_O + t * 64 + lane_sel;
+    const uint32_t tP = tmem_base + COL_P + t * 64 + lane_sel;
+    const float c = p.scale_log2;
+    const int my_items = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const uint32_t total_blocks = static_cast<uint32_t>(my_items) * n;
+    if (p.use_token && t == 1) asm volatile("bar.arrive %0, 256;" ::"r"(1) : "memory");      // warpgroup 0 owns the first token
+
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int q0, h, b;
+      item_coords(p, item, q0, h, b);
+      float m_ref = -INFINITY, l_run = 0.f;
+      // one KV block; `masked` selects the tail-block variant (keeps the compare/select instructions out of the common path)
+      auto block_body = [&](int j, auto masked) {
+        mbar_wait(&s_full[t], g & 1u);
+        tc_fence_after_sync();
+        uint32_t s[128];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(tS + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q * 32]));
+        bool pv_ok = g == 0;                                 // P_t / O_t are free once PV of the previous block retired (waited late)
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);              // S_t(g+1) may now overwrite S_t
+        if constexpr (decltype(masked)::value) {
+          const int kv_valid = p.S - j * BKV;
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv_valid) s[i] = 0xff800000u;           // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
+        const bool need = (mx - m_ref) * c > 8.0f;
+        float alpha = 1.0f;
+        if (need) {
+          alpha = fast_exp2((m_ref - mx) * c);              // 0 on the first block (m_ref = -inf)
+          m_ref = mx;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          if (!pv_ok) { mbar_wait(&pv_done[t], (g - 1) & 1u); pv_ok = true; }     // O_t is stable
+          tc_fence_after_sync();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tO + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(tO + cc * 32, v);
+          }
+          tmem_st_wait();
+        }
+        const float mb = m_ref * c;
+        // ping-pong token: MUFU phases of the two warpgroups alternate
+        if (p.use_token) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        uint32_t pk[64];
+        const float rsum = exp_row<kPolyMask>(s, pk, c, mb);
+        if (p.use_token && !(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
+        l_run = l_run * alpha + rsum;
+        if (!pv_ok) mbar_wait(&pv_done[t], (g - 1) & 1u);    // PV of the previous block has read P_t
+        tc_fence_after_sync();
+        tmem_st_32x32b_x32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_st_32x32b_x32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      };
+      for (int j = 0; j < n; ++j, ++g) {
+        if (p.S - j * BKV < BKV) block_body(j, std::true_type{});
+        else block_body(j, std::false_type{});
+      }
+      // epilogue: O_t / l  (attention.rs:334-343: 0 when the sum is <= 1e-10)
+      mbar_wait(&pv_done[t], (g - 1) & 1u);
+      tc_fence_after_sync();
+      const int row = q0 + t * BQ + r;
+      const float inv = l_run > 1e-10f ? 1.0f / l_run : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.S + row) * p.d + h * DH);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO + cc * 32, v);
+        tmem_ld_wait();
+        if (row < p.S) {
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * gg + 0]) * inv, __uint_as_float(v[8 * gg + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(v[8 * gg + 2]) * inv, __uint_as_float(v[8 * gg + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(v[8 * gg + 4]) * inv, __uint_as_float(v[8 * gg + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(v[8 * gg + 6]) * inv, __uint_as_float(v[8 * gg + 7]) * inv);
+            dst[cc * 4 + gg] = w;
+          }
+        }
+      }
+      tc_fence_before_sync();       // the next item's first PV (issued after this warpgroup's next p_full) overwrites O_t
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
+bool g_tm_init = false;
+int g_tm_sms = 0;
+
+template <int kPolyMask>
+int launch_tm(const CUtensorMap& tm, const AttnTmParams& p, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel<kPolyMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+    attr_set = true;
+  }
+  attention_tm_kernel<kPolyMask><<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p);
+  count_launch();
+  WB_CUDA_OK(cudaGetLastError());
+  return WB_OK;
+}
+
+}  // namespace
+
+int launch_attention_tm(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream) {
+  if (!g_tm_init) {
+    int dev = 0;
+    WB_CUDA_OK(cudaGetDevice(&dev));
+    WB_CUDA_OK(cudaDeviceGetAttribute(&g_tm_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_tm_init = true;
+  }
+  if (B <= 0 || S <= 0) return WB_OK;
+  if (d != n_heads * DH) return set_error(WB_ERR_MODEL, "attention kernel needs d_head == 64 (all Whisper sizes)");
+  CUtensorMap tm;      // one map serves Q, K and V tiles: box = 64 columns x 128 rows of the [B][S][3d] qkv buffer
+  int rc = make_tmap_bf16_3d(&tm, qkv, 3ull * d, S, B, 3ull * d * 2, 3ull * d * 2 * S, DH, BQ);
+  if (rc != WB_OK) return rc;
+  AttnTmParams p;
+  p.S = S;
+  p.d = d;
+  p.n_kv_blocks = (S + BKV - 1) / BKV;
+  p.n_qpairs = (S + 2 * BQ - 1) / (2 * BQ);
+  p.n_heads = n_heads;
+  p.n_items = B * n_heads * p.n_qpairs;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
+  p.out = out;
+  static const int no_token = getenv("WB_ATTN_NOTOKEN") != nullptr;
+  static const int poly = getenv("WB_ATTN_POLY") ? atoi(getenv("WB_ATTN_POLY")) : 0;      // tuning switch: 0, 1, 2 or 3 of every 8 exponentials
+  p.use_token = no_token ? 0 : 1;
+  const int grid = p.n_items < g_tm_sms ? p.n_items : g_tm_sms;
+  switch (poly) {
+    case 1: return launch_tm<0x10>(tm, p, grid, stream);
+    case 2: return launch_tm<0x11>(tm, p, grid, stream);
+    case 3: return launch_tm<0x49>(tm, p, grid, stream);
+    case 4: return launch_tm<0x55>(tm, p, grid, stream);
+    default: return launch_tm<0>(tm, p, grid, stream);
+  }
+}
+
+}  // namespace wb

@@ -912,6 +912,43 @@ int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_
   return cleanup(WB_OK);
 }
 
+int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int iters, float* ms_per_launch) {
+  int rc = debug_device(device);
+  if (rc != WB_OK) return rc;
+  if (!ms_per_launch || iters <= 0) return set_error(WB_ERR_MODEL, "bad argument");
+  DevBuf<float> f;
+  DevBuf<bf16> bq, bo;
+  auto cleanup = [&](int r) { f.release(); bq.release(); bo.release(); return r; };
+  const size_t per = static_cast<size_t>(S) * 3 * d, nq = per * B, no = static_cast<size_t>(B) * S * d;
+  if ((rc = f.ensure(per)) || (rc = bq.ensure(nq)) || (rc = bo.ensure(no))) return cleanup(rc);
+  std::vector<float> h(per);
+  uint32_t x = 12345u;
+  for (size_t i = 0; i < per; ++i) {                      // LCG noise in [-2, 2): scores with a realistic spread
+    x = x * 1664525u + 1013904223u;
+    h[i] = (static_cast<float>(x >> 8) / 8388608.0f - 1.0f) * 2.0f;
+  }
+  cudaMemcpy(f.p, h.data(), per * 4, cudaMemcpyHostToDevice);
+  launch_f32_to_bf16(f.p, bq.p, per, nullptr);
+  for (int b = 1; b < B; ++b) cudaMemcpyAsync(bq.p + b * per, bq.p, per * 2, cudaMemcpyDeviceToDevice, nullptr);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 2; ++i)
+    if ((rc = launch_attention(bq.p, bo.p, B, S, d, n_heads, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e0, nullptr);
+  for (int i = 0; i < iters; ++i)
+    if ((rc = launch_attention(bq.p, bo.p, B, S, d, n_heads, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e1, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("attention kernel failed: ") + cudaGetErrorString(e)));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+  return cleanup(WB_OK);
+}
+
 long long wb_launch_count(void) { return wb::g_launch_count.load(); }
 
 int wb_profile_enable(wb_model* m, int on) {
