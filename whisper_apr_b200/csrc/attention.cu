@@ -1,28 +1,29 @@
-// Non-causal multi-head self-attention on tcgen05 / TMEM, fed by TMA.
+// Non-causal multi-head self-attention on tcgen05 with the probabilities kept in TENSOR MEMORY.
 //
 // Replaces MultiHeadAttention::forward_cross_flash (src/model/attention.rs:894-935) with its per-head
 // flash_attention_simd (attention.rs:472-519) of the reference: heads are 64-wide column slices of q, k, v
 // (extract_head, attention.rs:1094-1107), scores are scaled by 1/sqrt(64), the softmax is the same online
-// (running max / running sum) recurrence, just over KV blocks of 64 instead of 32 -- block size does not
+// (running max / running sum) recurrence, just over KV blocks of 128 instead of 32 -- the block size does not
 // change the result (the reference asserts this itself, attention.rs:2186-2228).  The encoder passes no mask.
 //
-// Persistent warp-specialised kernel: one CTA per SM loops over work items (chunk, head, pair of 128-query tiles); 384 threads:
-//   warp 0      TMA producer: Q0/Q1 of the item (double buffered across items), then a 4-stage ring of K_j / V_j tiles
-//               ([64][64] bf16, 128 B swizzle); runs ahead of the consumers, also across item boundaries.
-//   warp 1      tcgen05.mma issuer of S_t[g&1] = Q_t K_j^T for both query tiles t: 4 x (128x64x16) each, both operands
-//               K-major, accumulators double buffered in TMEM, so S of the next block is ready before the softmax of the
-//               current block has finished.
-//   warps 2,3   tcgen05.mma issuers of O_t += P_t[g&1] V_j (one warp per tile): 4 x (128x64x16), A = P (smem),
-//               B = V_j used MN-major straight from its TMA tile.  (One issuing thread for everything was the
-//               bottleneck: ~20 dependent instructions per MMA on a single thread.)
-//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1: thread r owns query row r == TMEM lane r.
-//               One tcgen05.ld pass keeps the 64 scores of the row in registers; running max with LAZY rescaling
-//               (O_t in TMEM is rescaled only when the max grows by more than 2^8, a rare TMEM read-modify-write);
-//               p = exp2(s*c - m*c) -> bf16 -> K-major swizzled P_t tile (double buffered) in shared memory.
-//               The exponential phase is MUFU-bound; the two warpgroups pass a token through named barriers so their
-//               MUFU phases alternate while the other warpgroup does its barrier waits, tcgen05.ld and row max.
-// TMEM columns: S_t[b] at t*128 + b*64 (256 total), O_t at 256 + t*64.   smem: Q 64 KB + K/V ring 64 KB + P 64 KB.
-// The kernel is MUFU(ex2)-bound by construction: 2 x 8192 exponentials per (256 x 64) block at 16/clk/SM.
+// The exponential (MUFU.EX2, 16/clk/SM) is the binding pipe for d_head = 64 -- 2x the tensor time -- so everything that is
+// not an exponential has to hide behind one.  (The round's first kernel -- 64-key blocks, P staged through shared memory --
+// spent as long in barrier / fence / staging latency per block as in the exponentials: 0.72 ms per launch against 0.52 here.)
+//   * the KV block is 128 keys: half as many synchronisation rounds per exponential;
+//   * P never touches shared memory: the softmax warps write bf16 P straight back to TMEM (tcgen05.st) and the PV MMA takes
+//     its A operand from TMEM -- no st.shared, no generic->async proxy fence;
+//   * a softmax thread holds its whole 128-score row in registers (setmaxnreg moves registers from the four single-thread
+//     role warps to the two softmax warpgroups), so S_t is released right after the tcgen05.ld and the next QK^T runs
+//     under the exponentials of the current block;
+//   * the two softmax warpgroups (one per 128-query tile) alternate their exponential phases through a named-barrier token,
+//     so while one is MUFU-bound the other does its waits, loads, row max and P store.
+//
+// One persistent CTA per SM, work item = (chunk, head, pair of 128-query tiles), 384 threads:
+//   warp 0      TMA producer: Q0/Q1 (double buffered across items), ring of K_j / V_j tiles ([128][64] bf16, 128 B swizzle)
+//   warp 1      S_t = Q_t K_j^T issuer (4 x 128x128x16 per tile)
+//   warps 2,3   O_t += P_t V_j issuers (8 x 128x64x16, A = P_t in TMEM, B = V_j MN-major from its TMA tile)
+//   warps 4-7   softmax warpgroup of tile 0, warps 8-11 of tile 1; thread r owns query row r == TMEM lane r
+// TMEM columns: S_t at t*128 (256), O_t at 256 + t*64 (128), P_t at 384 + t*64 (128; 128 keys x bf16 = 64 columns).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -34,30 +35,24 @@
 namespace wb {
 namespace {
 
-constexpr int BQ = 128, BKV = 64, DH = 64;
+constexpr int BQ = 128, BKV = 128, DH = 64;
 constexpr int Q_TILE_BYTES = BQ * DH * 2;          // 16 KB
-constexpr int KV_TILE_BYTES = BKV * DH * 2;        // 8 KB
-constexpr int P_TILE_BYTES = BQ * BKV * 2;         // 16 KB
+constexpr int KV_TILE_BYTES = BKV * DH * 2;        // 16 KB
 constexpr int KV_STAGES = 4;
-constexpr int WS_THREADS = 384;
-constexpr int WS_SMEM = 4 * Q_TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 4 * P_TILE_BYTES + 256;
-constexpr int WS_TMEM_COLS = 512;
+constexpr int TM_THREADS = 384;
+constexpr int TM_SMEM = 4 * Q_TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 256;
+constexpr uint32_t TM_COLS = 512, COL_S = 0, COL_O = 256, COL_P = 384;
+constexpr int REGS_ROLE = 40, REGS_SOFTMAX = 232;   // 128*40 + 256*232 == 384*168
 
-struct AttnParams {
+struct AttnTmParams {
   int S, d, n_kv_blocks;
   int n_qpairs, n_heads, n_items;     // work items = B * n_heads * n_qpairs, q-pair fastest (neighbours share K/V through L2)
   float scale_log2;
   __nv_bfloat16* out;
-  long long* dbg;
   int use_token;
 };
 
-#define ATT_PROBE(i)                                                                                   \
-  do {                                                                                                 \
-    if (p.dbg && blockIdx.x == 5 && threadIdx.x == 128 && it == 1 && j == 10) p.dbg[i] = clock64();     \
-  } while (0)
-
-__device__ __forceinline__ void item_coords(const AttnParams& p, int item, int& q0, int& h, int& b) {
+__device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int& q0, int& h, int& b) {
   const int qp = item % p.n_qpairs;
   const int r = item / p.n_qpairs;
   h = r % p.n_heads;
@@ -65,22 +60,39 @@ __device__ __forceinline__ void item_coords(const AttnParams& p, int item, int& 
   q0 = qp * 2 * BQ;
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 1)
-attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+// exponentials of one 128-score row -> packed bf16 pairs (what tcgen05.st writes as P) and the row sum (four partial sums).
+// Measured alternatives that lost (tools/attn_bench.py, 32 x 20 x 1500 x 1500, ms per launch; this form: 0.517):
+// packed FFMA2/FADD2 in batches of 16 (0.625), scale+exponentials only under the token with the pack/sum after it (0.627),
+// a second warpgroup per tile on half the columns (0.69), 1-3 of every 8 exponentials as a polynomial on the FMA pipe (+2..+19 %).
+__device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb) {
+  float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    const float e0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), c, -mb));         // exp2(-inf) == 0: masked keys contribute nothing
+    const float e1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), c, -mb));
+    rs4[i & 3] += e0 + e1;
+    pk[i] = pack_bf16x2(e0, e1);
+  }
+  return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+}
+
+__global__ void __launch_bounds__(TM_THREADS, 1)
+attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;                                   // [qbuf][tile]
   uint8_t* sK = smem + 4 * Q_TILE_BYTES;                // [KV_STAGES]
   uint8_t* sV = sK + KV_STAGES * KV_TILE_BYTES;         // [KV_STAGES]
-  uint8_t* sP = sV + KV_STAGES * KV_TILE_BYTES;         // [tile][buf]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * P_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_TILE_BYTES);
   uint64_t* q_full = bars;                              // [2]
   uint64_t* q_empty = bars + 2;                         // [2]
-  uint64_t* kv_full = bars + 4;                         // [4]
-  uint64_t* kv_empty = bars + 8;                        // [4]
-  uint64_t* s_full = bars + 12;                         // [tile*2 + buf]
-  uint64_t* p_full = bars + 16;                         // [tile*2 + buf], 4 arrivals (one per warp)
-  uint64_t* pv_done = bars + 20;                        // [tile*2 + buf]
+  uint64_t* k_full = bars + 4;                          // [KV_STAGES]
+  uint64_t* v_full = bars + 8;                          // [KV_STAGES]
+  uint64_t* kv_empty = bars + 12;                       // [KV_STAGES]  3 arrivals: S issuer + two PV issuers
+  uint64_t* s_full = bars + 16;                         // [tile]
+  uint64_t* s_free = bars + 18;                         // [tile]  4 arrivals (one per softmax warp): S_t is in registers
+  uint64_t* p_full = bars + 20;                         // [tile]  4 arrivals: P_t is in TMEM
+  uint64_t* pv_done = bars + 22;                        // [tile]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5;
@@ -89,14 +101,13 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 3); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 3); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmQKV);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, WS_TMEM_COLS);
+    tmem_alloc(tmem_slot, TM_COLS);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -104,126 +115,122 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      uint32_t g = 0;                                   // running KV block counter across items
-      int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        int q0, h, b;
-        item_coords(p, item, q0, h, b);
-        const int qb = it & 1;
-        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[qb], 2 * Q_TILE_BYTES);
-        tma_load_3d(sQ + (qb * 2) * Q_TILE_BYTES, &tmQ, &q_full[qb], h * DH, q0, b);
-        tma_load_3d(sQ + (qb * 2 + 1) * Q_TILE_BYTES, &tmQ, &q_full[qb], h * DH, q0 + BQ, b);
-        for (int j = 0; j < n; ++j, ++g) {
-          const uint32_t st = g % KV_STAGES;
-          mbar_wait(&kv_empty[st], ((g / KV_STAGES) & 1u) ^ 1u);
-          mbar_expect_tx(&kv_full[st], 2 * KV_TILE_BYTES);
-          tma_load_3d(sK + st * KV_TILE_BYTES, &tmKV, &kv_full[st], p.d + h * DH, j * BKV, b);
-          tma_load_3d(sV + st * KV_TILE_BYTES, &tmKV, &kv_full[st], 2 * p.d + h * DH, j * BKV, b);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ S = Q K^T issuer (both tiles)
-      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0);
-      uint32_t g = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int qb = it & 1;
-        mbar_wait(&q_full[qb], (it >> 1) & 1);
-        const uint64_t qd0 = umma_desc_sw128(smem_u32(sQ + (qb * 2) * Q_TILE_BYTES));
-        const uint64_t qd1 = umma_desc_sw128(smem_u32(sQ + (qb * 2 + 1) * Q_TILE_BYTES));
-        for (int j = 0; j < n; ++j, ++g) {
-          const uint32_t st = g % KV_STAGES, buf = g & 1u;
-          mbar_wait(&kv_full[st], (g / KV_STAGES) & 1u);
-          if (g >= 2) {                                      // S_t[buf] was consumed by the softmax of block g-2
-            mbar_wait(&p_full[buf], ((g - 2) >> 1) & 1u);
-            mbar_wait(&p_full[2 + buf], ((g - 2) >> 1) & 1u);
+  if (warp < 4) {
+    reg_dealloc<REGS_ROLE>();
+    if (warp == 0) {
+      if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        uint32_t g = 0;                                   // running KV block counter across items
+        int it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+          int q0, h, b;
+          item_coords(p, item, q0, h, b);
+          const int qb = it & 1;
+          mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[qb], 2 * Q_TILE_BYTES);
+          tma_load_3d(sQ + (qb * 2) * Q_TILE_BYTES, &tmQKV, &q_full[qb], h * DH, q0, b);
+          tma_load_3d(sQ + (qb * 2 + 1) * Q_TILE_BYTES, &tmQKV, &q_full[qb], h * DH, q0 + BQ, b);
+          for (int j = 0; j < n; ++j, ++g) {
+            const uint32_t st = g % KV_STAGES;
+            mbar_wait(&kv_empty[st], ((g / KV_STAGES) & 1u) ^ 1u);
+            mbar_expect_tx(&k_full[st], KV_TILE_BYTES);
+            tma_load_3d(sK + st * KV_TILE_BYTES, &tmQKV, &k_full[st], p.d + h * DH, j * BKV, b);
+            mbar_expect_tx(&v_full[st], KV_TILE_BYTES);
+            tma_load_3d(sV + st * KV_TILE_BYTES, &tmQKV, &v_full[st], 2 * p.d + h * DH, j * BKV, b);
           }
-          tc_fence_after_sync();
-          const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * KV_TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + buf * 64, qd0 + 2 * k, kd + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[buf]);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + 128 + buf * 64, qd1 + 2 * k, kd + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[2 + buf]);
-          umma_commit(&kv_empty[st]);
         }
-        umma_commit(&q_empty[qb]);                           // every S MMA of this item has been issued
       }
-    }
-  } else if (warp < 4) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ O_t += P_t V issuer, one warp per tile
-      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, 1);     // B = V tile, MN-major
-      const int t = warp - 2;
-      uint32_t g = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        for (int j = 0; j < n; ++j, ++g) {
-          const uint32_t st = g % KV_STAGES, buf = g & 1u;
-          mbar_wait(&kv_full[st], (g / KV_STAGES) & 1u);
-          mbar_wait(&p_full[t * 2 + buf], (g >> 1) & 1u);    // P_t(g) is in smem
-          tc_fence_after_sync();
-          const uint64_t pd = umma_desc_sw128(smem_u32(sP + (t * 2 + buf) * P_TILE_BYTES));
-          const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * KV_TILE_BYTES));
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ------------------------------------------------------------------ S_t = Q_t K^T issuer (both tiles)
+        constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0);
+        uint32_t g = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+          const int qb = it & 1;
+          mbar_wait(&q_full[qb], (it >> 1) & 1);
+          const uint64_t qd[2] = {umma_desc_sw128(smem_u32(sQ + (qb * 2) * Q_TILE_BYTES)),
+                                  umma_desc_sw128(smem_u32(sQ + (qb * 2 + 1) * Q_TILE_BYTES))};
+          for (int j = 0; j < n; ++j, ++g) {
+            const uint32_t st = g % KV_STAGES;
+            mbar_wait(&k_full[st], (g / KV_STAGES) & 1u);
+            const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * KV_TILE_BYTES));
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) umma_f16(tmem_base + 256 + t * 64, pd + 2 * k, vd + 128 * k, idesc_o, (j | k) != 0);
-          umma_commit(&pv_done[t * 2 + buf]);
-          umma_commit(&kv_empty[st]);
+            for (int t = 0; t < 2; ++t) {
+              if (g >= 1) mbar_wait(&s_free[t], (g - 1) & 1u);         // the softmax warpgroup holds S_t(g-1) in registers
+              tc_fence_after_sync();
+#pragma unroll
+              for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + COL_S + t * 128, qd[t] + 2 * k, kd + 2 * k, idesc_s, k != 0);
+              umma_commit(&s_full[t]);
+            }
+            umma_commit(&kv_empty[st]);
+          }
+          umma_commit(&q_empty[qb]);                                    // every S MMA of this item has been issued
+        }
+      }
+    } else {
+      if (lane == 0) {
+        // ------------------------------------------------------------------ O_t += P_t V issuer, one warp per tile
+        constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, 1);        // B = V tile, MN-major
+        const int t = warp - 2;
+        const uint32_t tO = tmem_base + COL_O + t * 64;
+        const uint32_t tP = tmem_base + COL_P + t * 64;
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          for (int j = 0; j < n; ++j, ++g) {
+            const uint32_t st = g % KV_STAGES;
+            mbar_wait(&v_full[st], (g / KV_STAGES) & 1u);
+            mbar_wait(&p_full[t], g & 1u);                              // P_t(g) is in TMEM
+            tc_fence_after_sync();
+            const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * KV_TILE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k) umma_f16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_o, (j | k) != 0);
+            umma_commit(&pv_done[t]);
+            umma_commit(&kv_empty[st]);
+          }
         }
       }
     }
   } else {
+    reg_alloc<REGS_SOFTMAX>();
     // -------------------------------------------------------------------- softmax warpgroups
     const int t = (warp - 4) >> 2;                        // query tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;                 // row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + t * 128 + lane_sel;
-    const uint32_t tO = tmem_base + 256 + t * 64 + lane_sel;
-    const uint32_t p_row = smem_u32(sP + t * 2 * P_TILE_BYTES) + r * 128;
-    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const uint32_t tS = tmem_base + COL_S + t * 128 + lane_sel;
+    const uint32_t tO = tmem_base + COL_O + t * 64 + lane_sel;
+    const uint32_t tP = tmem_base + COL_P + t * 64 + lane_sel;
     const float c = p.scale_log2;
     const int my_items = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const uint32_t total_blocks = static_cast<uint32_t>(my_items) * n;
     if (p.use_token && t == 1) asm volatile("bar.arrive %0, 256;" ::"r"(1) : "memory");      // warpgroup 0 owns the first token
 
     uint32_t g = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       int q0, h, b;
       item_coords(p, item, q0, h, b);
       float m_ref = -INFINITY, l_run = 0.f;
-      // one KV block; `masked` selects the tail-block variant (keeps 128 compare/select instructions out of the common path)
+      // one KV block; `masked` selects the tail-block variant (keeps the compare/select instructions out of the common path)
       auto block_body = [&](int j, auto masked) {
-        const uint32_t buf = g & 1u;
-        ATT_PROBE(0);
-        mbar_wait(&s_full[t * 2 + buf], (g >> 1) & 1u);
+        mbar_wait(&s_full[t], g & 1u);
         tc_fence_after_sync();
-        ATT_PROBE(1);
-        uint32_t s0[32], s1[32];
-        tmem_ld_32x32b_x32(tS + buf * 64, s0);
-        tmem_ld_32x32b_x32(tS + buf * 64 + 32, s1);
-        // P_t[buf] is free once PV of block g-2 retired; probe early so the barrier latency hides behind the loads and the max
-        bool pv_ok = true;
-        if (g >= 2) pv_ok = mbar_try_wait(&pv_done[t * 2 + buf], ((g - 2) >> 1) & 1u);
-        tmem_ld_wait();
-        ATT_PROBE(2);
-        const int kv_valid = p.S - j * BKV;                 // >= 64 except in the last block
-        if constexpr (decltype(masked)::value) {
+        uint32_t s[128];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i >= kv_valid) s0[i] = 0xff800000u;         // -inf
-            if (32 + i >= kv_valid) s1[i] = 0xff800000u;
-          }
+        for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(tS + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q * 32]));
+        bool pv_ok = g == 0;                                 // P_t / O_t are free once PV of the previous block retired (waited late)
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);              // S_t(g+1) may now overwrite S_t
+        if constexpr (decltype(masked)::value) {
+          const int kv_valid = p.S - j * BKV;
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv_valid) s[i] = 0xff800000u;           // -inf
         }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+        for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])));
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
         const bool need = (mx - m_ref) * c > 8.0f;
@@ -232,9 +239,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           alpha = fast_exp2((m_ref - mx) * c);              // 0 on the first block (m_ref = -inf)
           m_ref = mx;
         }
-        ATT_PROBE(3);
         if (j > 0 && __any_sync(0xffffffffu, need)) {
-          mbar_wait(&pv_done[t * 2 + (buf ^ 1u)], ((g - 1) >> 1) & 1u);     // PV of the previous block retired: O_t is stable
+          if (!pv_ok) { mbar_wait(&pv_done[t], (g - 1) & 1u); pv_ok = true; }     // O_t is stable
           tc_fence_after_sync();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -247,46 +253,28 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           tmem_st_wait();
         }
-        if (!pv_ok) mbar_wait(&pv_done[t * 2 + buf], ((g - 2) >> 1) & 1u);
-        ATT_PROBE(4);
         const float mb = m_ref * c;
         // ping-pong token: MUFU phases of the two warpgroups alternate
         if (p.use_token) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-        ATT_PROBE(5);
-        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t pb = p_row + buf * P_TILE_BYTES;
-        auto emit = [&](const uint32_t (&sv)[32], int cgrp) {
-#pragma unroll
-          for (int gg = 0; gg < 4; ++gg) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = fast_exp2(__uint_as_float(sv[8 * gg + i]) * c - mb);   // exp2(-inf) == 0: masked
-            rs4[gg] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-            const uint32_t chunk = static_cast<uint32_t>(cgrp * 4 + gg);
-            const uint32_t addr = pb + ((chunk ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
-                         "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
-                         : "memory");
-          }
-        };
-        emit(s0, 0);
-        emit(s1, 1);
+        uint32_t pk[64];
+        const float rsum = exp_row(s, pk, c, mb);
         if (p.use_token && !(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
-        ATT_PROBE(6);
-        l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-        fence_proxy_async_smem();                           // generic-proxy P writes -> visible to the tensor core (async proxy)
+        l_run = l_run * alpha + rsum;
+        if (!pv_ok) mbar_wait(&pv_done[t], (g - 1) & 1u);    // PV of the previous block has read P_t
+        tc_fence_after_sync();
+        tmem_st_32x32b_x32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_st_32x32b_x32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+        tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
-        ATT_PROBE(7);
-        if (lane == 0) mbar_arrive(&p_full[t * 2 + buf]);
-        ATT_PROBE(8);
+        if (lane == 0) mbar_arrive(&p_full[t]);
       };
       for (int j = 0; j < n; ++j, ++g) {
         if (p.S - j * BKV < BKV) block_body(j, std::true_type{});
         else block_body(j, std::false_type{});
       }
       // epilogue: O_t / l  (attention.rs:334-343: 0 when the sum is <= 1e-10)
-      mbar_wait(&pv_done[t * 2 + ((g - 1) & 1u)], ((g - 1) >> 1) & 1u);
+      mbar_wait(&pv_done[t], (g - 1) & 1u);
       tc_fence_after_sync();
       const int row = q0 + t * BQ + r;
       const float inv = l_run > 1e-10f ? 1.0f / l_run : 0.f;
@@ -315,38 +303,34 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, WS_TMEM_COLS);
+    tmem_dealloc(tmem_base, TM_COLS);
   }
 }
 
-bool g_att_init = false;
-int g_att_sms = 0;
+bool g_tm_init = false;
+int g_tm_sms = 0;
 
 }  // namespace
 
 int attention_init() {
-  if (g_att_init) return WB_OK;
-  WB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+  if (g_tm_init) return WB_OK;
+  WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
   int dev = 0;
   WB_CUDA_OK(cudaGetDevice(&dev));
-  WB_CUDA_OK(cudaDeviceGetAttribute(&g_att_sms, cudaDevAttrMultiProcessorCount, dev));
-  g_att_init = true;
+  WB_CUDA_OK(cudaDeviceGetAttribute(&g_tm_sms, cudaDevAttrMultiProcessorCount, dev));
+  g_tm_init = true;
   return WB_OK;
 }
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream) {
-  static const bool old_kernel = getenv("WB_ATTN_OLD") != nullptr;      // A/B switch: attention_tm.cu is the product path
-  if (!old_kernel) return launch_attention_tm(qkv, out, B, S, d, n_heads, stream);
   int rc = attention_init();
   if (rc != WB_OK) return rc;
   if (B <= 0 || S <= 0) return WB_OK;
   if (d != n_heads * DH) return set_error(WB_ERR_MODEL, "attention kernel needs d_head == 64 (all Whisper sizes)");
-  CUtensorMap tq, tkv;
-  rc = make_tmap_bf16_3d(&tq, qkv, 3ull * d, S, B, 3ull * d * 2, 3ull * d * 2 * S, DH, BQ);
+  CUtensorMap tm;      // one map serves Q, K and V tiles: box = 64 columns x 128 rows of the [B][S][3d] qkv buffer
+  rc = make_tmap_bf16_3d(&tm, qkv, 3ull * d, S, B, 3ull * d * 2, 3ull * d * 2 * S, DH, BQ);
   if (rc != WB_OK) return rc;
-  rc = make_tmap_bf16_3d(&tkv, qkv, 3ull * d, S, B, 3ull * d * 2, 3ull * d * 2 * S, DH, BKV);
-  if (rc != WB_OK) return rc;
-  AttnParams p;
+  AttnTmParams p;
   p.S = S;
   p.d = d;
   p.n_kv_blocks = (S + BKV - 1) / BKV;
@@ -355,24 +339,12 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S,
   p.n_items = B * n_heads * p.n_qpairs;
   p.scale_log2 = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
   p.out = out;
-  p.dbg = nullptr;
-  p.use_token = getenv("WB_ATTN_NOTOKEN") ? 0 : 1;
-  if (getenv("WB_ATTN_PROBE")) {
-    static long long* d_dbg = nullptr;
-    if (!d_dbg) cudaMalloc(&d_dbg, 16 * sizeof(long long));
-    p.dbg = d_dbg;
-  }
-  const int grid = p.n_items < g_att_sms ? p.n_items : g_att_sms;
-  attention_ws_kernel<<<grid, WS_THREADS, WS_SMEM, stream>>>(tq, tkv, p);
+  static const int no_token = getenv("WB_ATTN_NOTOKEN") != nullptr;       // tuning switch
+  p.use_token = no_token ? 0 : 1;
+  const int grid = p.n_items < g_tm_sms ? p.n_items : g_tm_sms;
+  attention_tm_kernel<<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
-  if (p.dbg) {
-    cudaStreamSynchronize(stream);
-    long long hh[16];
-    cudaMemcpy(hh, p.dbg, sizeof hh, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[attn probe] wait_s %lld ldtm %lld max %lld pvwait %lld token %lld exp %lld fence %lld arrive %lld | block %lld\n", hh[1] - hh[0],
-            hh[2] - hh[1], hh[3] - hh[2], hh[4] - hh[3], hh[5] - hh[4], hh[6] - hh[5], hh[7] - hh[6], hh[8] - hh[7], hh[8] - hh[0]);
-  }
   return WB_OK;
 }
 

@@ -65,8 +65,6 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 // ---- attention: qkv bf16 [B][S][3d] (q | k | v column blocks) -> out bf16 [B][S][d]
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream);
 int attention_init();
-// same contract, P kept in tensor memory, 128-key blocks (attention_tm.cu) -- the product path
-int launch_attention_tm(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream);
 
 // ---- mel
 struct MelTables {                 // device-resident, built at model load
