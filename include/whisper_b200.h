@@ -142,6 +142,9 @@ void wb_debug_fft400_power_host(const float* y400, float* p201);
  * (A, W as f32, rounded to bf16 on upload; out as f32).  epilogue: see GemmEpilogue in wb_internal.h. */
 int wb_debug_gemm(int device, const float* A, const float* W, const float* bias, const float* resid_or_pe, int M, int N,
                   int K, int epilogue, float alpha, float* out);
+/* Times `iters` back-to-back launches of one GEMM shape ([n_batch][rows][K] x [N][K]^T, bf16, device-resident pseudo-random
+ * operands, bias on) after 2 warm-up launches; *ms_per_launch receives the mean.  Kernel tuning only. */
+int wb_debug_gemm_bench(int device, int n_batch, int rows, int N, int K, int epilogue, int iters, float* ms_per_launch);
 /* One attention call: qkv f32 [B][S][3d] (rounded to bf16) -> out f32 [B][S][d]. */
 int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_heads, float* out);
 /* Times `iters` back-to-back attention launches on device-resident pseudo-random bf16 qkv [B][S][3d] (CUDA events on the

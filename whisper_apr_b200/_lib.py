@@ -52,6 +52,7 @@ SIGNATURES = {
     "wb_debug_fft400_power_host": (None, [_vp, _vp]),
     "wb_debug_gemm": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp]),
     "wb_debug_attention": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "wb_debug_gemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "wb_debug_attention_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "wb_debug_encode": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int, _vp, C.c_size_t]),
     "wb_launch_count": (C.c_longlong, []),

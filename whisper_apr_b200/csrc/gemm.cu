@@ -124,6 +124,55 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, const uint3
   }
 }
 
+// Epilogue of one 32-column chunk for the CTA-pair kernel: acc = v * scale[n] + bias[n] with scale (alpha x per-column
+// dequantisation scale) and bias staged in shared memory once per tile (a global load per chunk stalled the epilogue warps
+// for an L2 round trip eight times per tile), and the residual row prefetched one chunk ahead.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&v)[32], long long out_row, int r_in_batch, int n0,
+                                               const float* s_scale, const float* s_bias) {
+  float acc[32];
+  const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+  const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 sc = sc4[i], bi = bi4[i];
+    acc[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, bi.x);
+    acc[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, bi.y);
+    acc[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, bi.z);
+    acc[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, bi.w);
+  }
+  if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_PE_F32) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = gelu_fast(acc[i]);
+  }
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 w;
+      w.x = pack_bf16x2(acc[8 * i + 0], acc[8 * i + 1]);
+      w.y = pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]);
+      w.z = pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]);
+      w.w = pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]);
+      o4[i] = w;
+    }
+  } else {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldc + n0);
+    static_assert(EPI != EPI_RESID_F32, "the residual epilogue goes through the TMA reduction");
+    if constexpr (EPI == EPI_GELU_PE_F32) {
+      const float4* pe4 = reinterpret_cast<const float4*>(p.pe + static_cast<long long>(r_in_batch) * p.N + n0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 e = __ldg(pe4 + i);
+        o4[i] = make_float4(acc[4 * i + 0] + e.x, acc[4 * i + 1] + e.y, acc[4 * i + 2] + e.z, acc[4 * i + 3] + e.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o4[i] = make_float4(acc[4 * i + 0], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
@@ -261,20 +310,24 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's half of the W tile
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
+  static constexpr int EPI_BYTES = 2 * 2 * BN * 4;        // per-tile scale and bias vectors, double buffered
+  static constexpr int STAGE_C_BYTES = 4 * 32 * 32 * 4;   // one 32 x 32 f32 staging tile per epilogue warp (TMA reduce-add source)
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + STAGE_C_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                const GemmKParams p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint8_t* sC = sB + STAGES * Cfg::B_BYTES;             // [4 epilogue warps][32 rows][128 B], 128 B swizzle (1024 B aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + Cfg::STAGE_C_BYTES);
   uint64_t* full = bars;                       // used in the leader only (both CTAs' TMA bytes land here)
   uint64_t* empty = bars + STAGES;             // per CTA, signalled by the leader's multicast commit
   uint64_t* tfull = bars + 2 * STAGES;         // per CTA, multicast commit
@@ -293,6 +346,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI == EPI_RESID_F32) tma_prefetch_desc(&tmC);
   }
   if (warp == 1) {
     tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
@@ -362,6 +416,11 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5 of both CTAs)
     const int q = warp & 3;
+    const int et = static_cast<int>(threadIdx.x) - 64;      // 0..127 among the epilogue threads
+    float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);    // [2][BN]
+    float* s_bias = s_scale + 2 * BN;                                                                 // [2][BN]
+    constexpr int NCH = BN / 32;
+    constexpr bool kResid = EPI == EPI_RESID_F32;
     uint32_t it = 0;
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
       const uint32_t buf = it & 1u;
@@ -373,20 +432,71 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int r_in_batch = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
       const bool row_ok = r_in_batch < p.rows_per_batch;
       const long long out_row = static_cast<long long>(b) * p.out_rows_per_batch + p.out_row_off + r_in_batch;
+      // stage this tile's per-column scale (alpha x dequantisation scale) and bias; columns past N get 0
+      float* sc = s_scale + buf * BN;
+      float* bi = s_bias + buf * BN;
+      for (int i = et; i < BN; i += 128) {
+        const int nn = nb * BN + i;
+        const bool ok = nn < p.N;
+        sc[i] = ok ? p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + nn) : 1.0f) : 0.f;
+        bi[i] = (ok && p.bias != nullptr) ? __ldg(p.bias + nn) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // scale / bias visible to the four epilogue warps
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
-        tmem_ld_wait();
+      // EPI_RESID_F32: the 32 x 32 f32 chunk is staged in shared memory (128 B swizzle: conflict-free 16 B stores) and added to
+      // the residual stream by a TMA reduction -- the L2 does the read-modify-write, rows past the end of the batch entry are
+      // clipped by the tensor map.  (Row-per-lane global loads/stores cost 32 L1 wavefronts per instruction: 16k cycles per
+      // tile, more than the whole K = 1280 mainloop.)
+      uint8_t* stage = sC + q * (32 * 32 * 4);
+      const uint32_t stage_row = smem_u32(stage) + lane * 128;
+      const int row0_in_batch = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32;
+      auto process = [&](const uint32_t (&v)[32], int c) {
         const int n0 = nb * BN + c * 32;
-        if (row_ok && n0 < p.N) epilogue_store<EPI>(p, v, out_row, r_in_batch, n0);
+        if (n0 >= p.N) return;
+        if constexpr (kResid) {
+          if (row0_in_batch >= p.rows_per_batch) return;      // warp-uniform: nothing of this warp's rows exists
+          const float4* sc4 = reinterpret_cast<const float4*>(sc + c * 32);
+          const float4* bi4 = reinterpret_cast<const float4*>(bi + c * 32);
+          if (lane == 0) tma_store_wait_read<0>();            // the previous chunk's reduction has read the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 s4 = sc4[i], b4 = bi4[i];
+            const float x0 = fmaf(__uint_as_float(v[4 * i + 0]), s4.x, b4.x), x1 = fmaf(__uint_as_float(v[4 * i + 1]), s4.y, b4.y);
+            const float x2 = fmaf(__uint_as_float(v[4 * i + 2]), s4.z, b4.z), x3 = fmaf(__uint_as_float(v[4 * i + 3]), s4.w, b4.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((static_cast<uint32_t>(i) ^ (lane & 7u)) << 4)), "f"(x0),
+                         "f"(x1), "f"(x2), "f"(x3)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&tmC, stage, n0, row0_in_batch, b);
+            tma_store_commit();
+          }
+        } else {
+          if (row_ok) epilogue_chunk<EPI>(p, v, out_row, r_in_batch, n0, sc + c * 32, bi + c * 32);
+        }
+      };
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32b_x32(t_row, v0);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v1);
+        process(v0, c);
+        tmem_ld_wait();
+        if (c + 2 < NCH) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
+        process(v1, c + 1);
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+    }
+    if constexpr (kResid) {
+      if (lane == 0) tma_store_wait_all();     // every reduction of this warp has been performed before the CTA exits
     }
   }
 
@@ -420,7 +530,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKPara
 }
 
 template <int BN, int EPI>
-int launch_variant2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, int num_tiles2, cudaStream_t stream) {
+int launch_variant2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKParams& kp, int num_tiles2, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     WB_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM));
@@ -428,20 +538,20 @@ int launch_variant2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKPar
   }
   int pairs = g_num_sms / 2;
   if (num_tiles2 < pairs) pairs = num_tiles2;
-  gemm2_tn_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM, stream>>>(ta, tb, kp);
+  gemm2_tn_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM, stream>>>(ta, tb, tc, kp);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
 
 template <int BN>
-int launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, int num_tiles2, cudaStream_t s) {
+int launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKParams& kp, int num_tiles2, cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_variant2<BN, EPI_BF16>(ta, tb, kp, num_tiles2, s);
-    case EPI_GELU_BF16: return launch_variant2<BN, EPI_GELU_BF16>(ta, tb, kp, num_tiles2, s);
-    case EPI_RESID_F32: return launch_variant2<BN, EPI_RESID_F32>(ta, tb, kp, num_tiles2, s);
-    case EPI_GELU_PE_F32: return launch_variant2<BN, EPI_GELU_PE_F32>(ta, tb, kp, num_tiles2, s);
-    case EPI_F32: return launch_variant2<BN, EPI_F32>(ta, tb, kp, num_tiles2, s);
+    case EPI_BF16: return launch_variant2<BN, EPI_BF16>(ta, tb, tc, kp, num_tiles2, s);
+    case EPI_GELU_BF16: return launch_variant2<BN, EPI_GELU_BF16>(ta, tb, tc, kp, num_tiles2, s);
+    case EPI_RESID_F32: return launch_variant2<BN, EPI_RESID_F32>(ta, tb, tc, kp, num_tiles2, s);
+    case EPI_GELU_PE_F32: return launch_variant2<BN, EPI_GELU_PE_F32>(ta, tb, tc, kp, num_tiles2, s);
+    case EPI_F32: return launch_variant2<BN, EPI_F32>(ta, tb, tc, kp, num_tiles2, s);
   }
   return set_error(WB_ERR_MODEL, "unknown GEMM epilogue");
 }
@@ -495,6 +605,19 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   return WB_OK;
 }
 
+// f32 [d2][d1][d0] output view for the TMA reduction of the residual epilogue (128 B swizzle, box0 * 4 == 128 bytes)
+static int make_tmap_f32_3d(CUtensorMap* out, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                            uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, d2 > 1 ? stride2_bytes : stride1_bytes * d1};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(WB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the f32 output view (" + std::to_string(static_cast<int>(r)) + ")");
+  return WB_OK;
+}
+
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   int rc = gemm_init();
   if (rc != WB_OK) return rc;
@@ -527,8 +650,15 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.pe = g.pe;
   if (!one_cta) {
     const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
-    if (BN == 256) return launch_bn2<256>(g.epilogue, ta, tb, kp, num_tiles2, stream);
-    return launch_bn2<128>(g.epilogue, ta, tb, kp, num_tiles2, stream);
+    CUtensorMap tc = ta;                                  // only the residual epilogue reads it
+    if (g.epilogue == EPI_RESID_F32) {
+      float* base = static_cast<float*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
+      rc = make_tmap_f32_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 4,
+                            static_cast<uint64_t>(g.out_rows_per_batch) * g.ldc * 4, 32, 32);
+      if (rc != WB_OK) return rc;
+    }
+    if (BN == 256) return launch_bn2<256>(g.epilogue, ta, tb, tc, kp, num_tiles2, stream);
+    return launch_bn2<128>(g.epilogue, ta, tb, tc, kp, num_tiles2, stream);
   }
   const int num_tiles = kp.n_batch * kp.tiles_m_per_batch * kp.tiles_n;
   if (BN == 256) return launch_bn<256>(g.epilogue, ta, tb, kp, num_tiles, stream);

@@ -912,6 +912,57 @@ int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_
   return cleanup(WB_OK);
 }
 
+int wb_debug_gemm_bench(int device, int n_batch, int rows, int N, int K, int epilogue, int iters, float* ms_per_launch) {
+  int rc = debug_device(device);
+  if (rc != WB_OK) return rc;
+  if (!ms_per_launch || iters <= 0) return set_error(WB_ERR_MODEL, "bad argument");
+  DevBuf<float> f, fb, fo;
+  DevBuf<bf16> ba, bw, bo;
+  auto cleanup = [&](int r) { f.release(); fb.release(); fo.release(); ba.release(); bw.release(); bo.release(); return r; };
+  const size_t M = static_cast<size_t>(n_batch) * rows, na = M * K, nw = static_cast<size_t>(N) * K, no = M * N;
+  const size_t nf = std::max(static_cast<size_t>(rows) * K, nw);
+  const bool bf_out = epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16;
+  if ((rc = f.ensure(nf)) || (rc = fb.ensure(N)) || (rc = ba.ensure(na)) || (rc = bw.ensure(nw)) ||
+      (rc = bf_out ? bo.ensure(no) : fo.ensure(no)))
+    return cleanup(rc);
+  std::vector<float> h(nf);
+  uint32_t x = 777u;
+  for (size_t i = 0; i < nf; ++i) {
+    x = x * 1664525u + 1013904223u;
+    h[i] = (static_cast<float>(x >> 8) / 8388608.0f - 1.0f) * 0.05f;
+  }
+  cudaMemcpy(f.p, h.data(), nf * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(fb.p, h.data(), static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice);
+  launch_f32_to_bf16(f.p, bw.p, nw, nullptr);
+  launch_f32_to_bf16(f.p, ba.p, static_cast<size_t>(rows) * K, nullptr);
+  for (int b = 1; b < n_batch; ++b)
+    cudaMemcpyAsync(ba.p + static_cast<size_t>(b) * rows * K, ba.p, static_cast<size_t>(rows) * K * 2, cudaMemcpyDeviceToDevice, nullptr);
+  if (!bf_out) cudaMemsetAsync(fo.p, 0, no * 4, nullptr);
+  GemmDesc g{};
+  g.A = ba.p; g.a_row_stride = K; g.a_batch_stride = static_cast<long long>(rows) * K; g.rows_per_batch = rows; g.n_batch = n_batch;
+  g.W = bw.p; g.N = N; g.K = K; g.epilogue = epilogue; g.alpha = 1.0f; g.col_scale = nullptr; g.bias = fb.p;
+  g.ldc = N; g.out_rows_per_batch = rows; g.out_row_off = 0; g.pe = nullptr;
+  g.out = bf_out ? static_cast<void*>(bo.p) : static_cast<void*>(fo.p);
+  if (epilogue == EPI_GELU_PE_F32) return cleanup(set_error(WB_ERR_MODEL, "pe epilogue not benchmarked"));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 2; ++i)
+    if ((rc = launch_gemm(g, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e0, nullptr);
+  for (int i = 0; i < iters; ++i)
+    if ((rc = launch_gemm(g, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e1, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("gemm kernel failed: ") + cudaGetErrorString(e)));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+  return cleanup(WB_OK);
+}
+
 int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int iters, float* ms_per_launch) {
   int rc = debug_device(device);
   if (rc != WB_OK) return rc;
