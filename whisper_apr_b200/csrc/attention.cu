@@ -63,7 +63,10 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 // exponentials of one 128-score row -> packed bf16 pairs (what tcgen05.st writes as P) and the row sum (four partial sums).
 // Measured alternatives that lost (tools/attn_bench.py, 32 x 20 x 1500 x 1500, ms per launch; this form: 0.517):
 // packed FFMA2/FADD2 in batches of 16 (0.625), scale+exponentials only under the token with the pack/sum after it (0.627),
-// a second warpgroup per tile on half the columns (0.69), 1-3 of every 8 exponentials as a polynomial on the FMA pipe (+2..+19 %).
+// a second warpgroup per tile on half the columns (0.69), 1-3 of every 8 exponentials as a polynomial on the FMA pipe (+2..+19 %),
+// a run-time loop over 32-column chunks re-read from TMEM with the pack/sum one iteration behind the exponentials (0.60).
+// ncu: a lone warp per scheduler issues back-to-back MUFU.EX2 every ~9.5 cycles (8 with two warps), and ptxas places each
+// FADD two instructions behind the MUFU pair it consumes, so the phase runs at ~11 cycles per exponential (72 % of the pipe).
 __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb) {
   float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
