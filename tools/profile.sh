@@ -8,8 +8,10 @@ $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -20 g
 tail -c 600 gpurun_out/${TAG}_plain.log
 # every launch of the LAST (timed + profiled) steps with its device time
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
-for K in ${KERNELS:-attention_kernel gemm_tn_kernel mel_stft_kernel}; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -s ${SKIP:-20} -c 2 -f -o gpurun_out/${TAG}_$K $CMD > gpurun_out/${TAG}_ncu_$K.log 2>&1
+# kernel regex : launches to skip (warm-up) : launches to capture
+for SPEC in ${KERNELS:-attention_tm_kernel:20:1 gemm2_tn_kernel:40:4 mel_stft_kernel:2:1 layernorm_kernel:20:1}; do
+  K=${SPEC%%:*}; REST=${SPEC#*:}; S=${REST%%:*}; C=${REST#*:}
+  ncu --set full --clock-control none --import-source on -k regex:$K -s $S -c $C -f -o gpurun_out/${TAG}_$K $CMD > gpurun_out/${TAG}_ncu_$K.log 2>&1
   tail -2 gpurun_out/${TAG}_ncu_$K.log
 done
 ls -la gpurun_out/ | tail -12

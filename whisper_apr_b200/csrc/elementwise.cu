@@ -112,6 +112,46 @@ __global__ void i4_to_bf16_kernel(const uint8_t* __restrict__ in, __nv_bfloat16*
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) out[i] = __float2bfloat16_rn(static_cast<float>(unpack_i4(in[i >> 1], i)));
 }
+// Vector forms used by the per-layer weight expansion (n % 32 == 0, 16-byte aligned): 16 B of packed payload per thread.
+__device__ __forceinline__ uint32_t bf16x2_from_ints(int lo, int hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(static_cast<float>(lo), static_cast<float>(hi));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__global__ void __launch_bounds__(256) i8_to_bf16_vec_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n16) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n16; i += stride) {
+    const uint4 v = __ldg(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = bf16x2_from_ints(static_cast<int8_t>(w[k] & 0xff), static_cast<int8_t>((w[k] >> 8) & 0xff));
+      o[2 * k + 1] = bf16x2_from_ints(static_cast<int8_t>((w[k] >> 16) & 0xff), static_cast<int8_t>(w[k] >> 24));
+    }
+    out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+__global__ void __launch_bounds__(256) i4_to_bf16_vec_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n16) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n16; i += stride) {
+    const uint4 v = __ldg(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                  // one 32-bit word = 8 nibbles = 8 weights, low nibble first
+      uint32_t o[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int lo = (static_cast<int>(w[k] << (28 - 8 * b))) >> 28;          // sign-extended nibble 2b
+        const int hi = (static_cast<int>(w[k] << (24 - 8 * b))) >> 28;          // sign-extended nibble 2b + 1
+        o[b] = bf16x2_from_ints(lo, hi);
+      }
+      out[4 * i + k] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
 __global__ void i8_to_f32_kernel(const int8_t* __restrict__ in, float scale, float* __restrict__ out, size_t n) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -183,6 +223,12 @@ int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream
 }
 int launch_i8_to_bf16(const int8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
   if (n == 0) return WB_OK;
+  if (n % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    i8_to_bf16_vec_kernel<<<grid_for(n / 16), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n / 16);
+    count_launch();
+    WB_CUDA_OK(cudaGetLastError());
+    return WB_OK;
+  }
   i8_to_bf16_kernel<<<grid_for(n), 256, 0, s>>>(in, out, n);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
@@ -190,6 +236,12 @@ int launch_i8_to_bf16(const int8_t* in, __nv_bfloat16* out, size_t n, cudaStream
 }
 int launch_i4_to_bf16(const uint8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
   if (n == 0) return WB_OK;
+  if (n % 32 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    i4_to_bf16_vec_kernel<<<grid_for(n / 32), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n / 32);
+    count_launch();
+    WB_CUDA_OK(cudaGetLastError());
+    return WB_OK;
+  }
   i4_to_bf16_kernel<<<grid_for(n), 256, 0, s>>>(in, out, n);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());

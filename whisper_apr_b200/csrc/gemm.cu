@@ -346,7 +346,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if constexpr (EPI == EPI_RESID_F32) tma_prefetch_desc(&tmC);
+    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BF16 || EPI == EPI_GELU_BF16) tma_prefetch_desc(&tmC);
   }
   if (warp == 1) {
     tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
@@ -480,23 +480,68 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (row_ok) epilogue_chunk<EPI>(p, v, out_row, r_in_batch, n0, sc + c * 32, bi + c * 32);
         }
       };
+      // bf16 outputs: two 32-column chunks make one 32 x 64 bf16 (128 B per row) staging tile, written with conflict-free 16 B
+      // shared-memory stores and sent out by one TMA store.  Row-per-lane STG.128 costs 32 L1 wavefronts per instruction, and the
+      // L1 / shared-memory data pipe is already ~full with the TMA operand writes and the tensor core's operand reads.
+      constexpr bool kBf16Out = EPI == EPI_BF16 || EPI == EPI_GELU_BF16;
+      auto half_bf16 = [&](const uint32_t (&v)[32], int c, int half) {
+        const float4* sc4 = reinterpret_cast<const float4*>(sc + c * 32);
+        const float4* bi4 = reinterpret_cast<const float4*>(bi + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                         // 8 columns -> one 16 B store
+          const float4 s0 = sc4[2 * i], b0 = bi4[2 * i], s1 = sc4[2 * i + 1], b1 = bi4[2 * i + 1];
+          float a[8];
+          a[0] = fmaf(__uint_as_float(v[8 * i + 0]), s0.x, b0.x); a[1] = fmaf(__uint_as_float(v[8 * i + 1]), s0.y, b0.y);
+          a[2] = fmaf(__uint_as_float(v[8 * i + 2]), s0.z, b0.z); a[3] = fmaf(__uint_as_float(v[8 * i + 3]), s0.w, b0.w);
+          a[4] = fmaf(__uint_as_float(v[8 * i + 4]), s1.x, b1.x); a[5] = fmaf(__uint_as_float(v[8 * i + 5]), s1.y, b1.y);
+          a[6] = fmaf(__uint_as_float(v[8 * i + 6]), s1.z, b1.z); a[7] = fmaf(__uint_as_float(v[8 * i + 7]), s1.w, b1.w);
+          if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = gelu_fast(a[k]);
+          }
+          const uint32_t j = static_cast<uint32_t>(half * 4 + i);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pack_bf16x2(a[0], a[1])),
+                       "r"(pack_bf16x2(a[2], a[3])), "r"(pack_bf16x2(a[4], a[5])), "r"(pack_bf16x2(a[6], a[7]))
+                       : "memory");
+        }
+      };
       uint32_t v0[32], v1[32];
       tmem_ld_32x32b_x32(t_row, v0);
 #pragma unroll 1
       for (int c = 0; c < NCH; c += 2) {
         tmem_ld_wait();
         tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v1);
-        process(v0, c);
-        tmem_ld_wait();
-        if (c + 2 < NCH) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
-        process(v1, c + 1);
+        if constexpr (kBf16Out) {
+          const bool live = nb * BN + c * 32 < p.N && row0_in_batch < p.rows_per_batch;       // warp-uniform
+          if (live) {
+            if (lane == 0) tma_store_wait_read<0>();          // the previous pair's store has read the staging tile
+            __syncwarp();
+            half_bf16(v0, c, 0);
+          }
+          tmem_ld_wait();
+          if (c + 2 < NCH) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
+          if (live) {
+            half_bf16(v1, c + 1, 1);                          // columns past N (N % 64 == 32) are clipped by the tensor map
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, stage, nb * BN + c * 32, row0_in_batch, b);
+              tma_store_commit();
+            }
+          }
+        } else {
+          process(v0, c);
+          tmem_ld_wait();
+          if (c + 2 < NCH) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
+          process(v1, c + 1);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[buf]);
     }
-    if constexpr (kResid) {
-      if (lane == 0) tma_store_wait_all();     // every reduction of this warp has been performed before the CTA exits
+    if constexpr (kResid || EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
+      if (lane == 0) tma_store_wait_all();     // every store / reduction of this warp has been performed before the CTA exits
     }
   }
 
@@ -650,7 +695,14 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.pe = g.pe;
   if (!one_cta) {
     const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
-    CUtensorMap tc = ta;                                  // only the residual epilogue reads it
+    CUtensorMap tc = ta;                                  // the f32 debug / positional-embedding epilogues do not read it
+    if (g.epilogue == EPI_BF16 || g.epilogue == EPI_GELU_BF16) {
+      __nv_bfloat16* base = static_cast<__nv_bfloat16*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
+      rc = make_tmap_bf16_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 2,
+                             g.n_batch > 1 ? static_cast<uint64_t>(g.out_rows_per_batch) * g.ldc * 2 : static_cast<uint64_t>(g.ldc) * 2 * g.rows_per_batch,
+                             64, 32);
+      if (rc != WB_OK) return rc;
+    }
     if (g.epilogue == EPI_RESID_F32) {
       float* base = static_cast<float*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
       rc = make_tmap_f32_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 4,

@@ -63,6 +63,9 @@ struct LayerW {
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float* sqkv = nullptr;                 // [3d] per-column scale (quantised files) or nullptr
   float so = 1.f, s1 = 1.f, s2 = 1.f;    // per-tensor scales
+  // Int8 / Int4 `.apr` payloads stay PACKED in HBM (the file's own bytes: i8, or two's-complement nibbles, low nibble first);
+  // the bf16 pointers above then alias the model's per-kind expansion buffers, refilled for every layer (see expand_layer).
+  uint8_t *pqkv = nullptr, *po = nullptr, *p1 = nullptr, *p2 = nullptr;
 };
 
 struct Workspace {
@@ -90,6 +93,8 @@ struct wb_model {
   float conv1_s = 1.f, conv2_s = 1.f;
   float* pe = nullptr;
   std::vector<wb::LayerW> layers;
+  int quant = 0;                        // 0: f32 payloads (bf16 weights resident); 2 / 3: int8 / int4 payloads resident, expanded per layer
+  wb::bf16 *xp_qkv = nullptr, *xp_o = nullptr, *xp_1 = nullptr, *xp_2 = nullptr;   // expansion buffers (12 d^2 bf16: L2-sized)
   float *lnp_g = nullptr, *lnp_b = nullptr;
   wb::Workspace ws;
   // per-kernel timing (wb_profile_*): CUDA events recorded on the launching stream around every launch
@@ -184,6 +189,21 @@ struct Uploader {
     }
     if (rc != WB_OK) return rc;
     WB_CUDA_OK(cudaStreamSynchronize(m->stream));      // staging is reused by the next tensor
+    return WB_OK;
+  }
+  // Quantised GEMM weight: the payload bytes go to the device unchanged (dst pre-zeroed; absent / short tensors keep zeros).
+  int load_packed(const std::string& name, uint8_t* dst, size_t count, float* scale_out) {
+    *scale_out = 1.f;
+    const AprTensor* t = f->find(name);
+    if (!t) return WB_OK;
+    size_t nbytes = 0;
+    const uint8_t* src = f->payload(*t, &nbytes);
+    if (!src) return WB_OK;
+    const size_t n = std::min<size_t>(static_cast<size_t>(t->n_elements), count);
+    if (n == 0) return WB_OK;
+    const size_t copy_bytes = f->cfg.quantization == 2 ? n : n / 2;     // a trailing odd nibble (never for these shapes) is dropped
+    WB_CUDA_OK(cudaMemcpyAsync(dst, src, copy_bytes, cudaMemcpyHostToDevice, m->stream));
+    *scale_out = t->scale;
     return WB_OK;
   }
   // GEMM weight -> bf16 (quantised payloads keep their integer value; *scale_out carries the per-tensor scale).
@@ -306,6 +326,12 @@ int load_weights(wb_model* m, const AprFile& f) {
     if ((rc = up.load_f32(name, m->pe, ctx * d)) != WB_OK) return done(rc);
   }
 
+  m->quant = quant ? static_cast<int>(f.cfg.quantization) : 0;
+  if (quant) {
+    if ((rc = dev_alloc(m, 3 * d * d, &m->xp_qkv)) != WB_OK || (rc = dev_alloc(m, d * d, &m->xp_o)) != WB_OK ||
+        (rc = dev_alloc(m, 4 * d * d, &m->xp_1)) != WB_OK || (rc = dev_alloc(m, 4 * d * d, &m->xp_2)) != WB_OK)
+      return done(rc);
+  }
   m->layers.resize(L);
   for (size_t i = 0; i < L; ++i) {
     LayerW& w = m->layers[i];
@@ -315,6 +341,37 @@ int load_weights(wb_model* m, const AprFile& f) {
     if ((rc = new_f32_param(m, up, p + ".final_layer_norm.weight", d, 1.f, &w.ln2_g)) != WB_OK) return done(rc);
     if ((rc = new_f32_param(m, up, p + ".final_layer_norm.bias", d, 0.f, &w.ln2_b)) != WB_OK) return done(rc);
     // fused QKV: rows [0,d) = q_proj, [d,2d) = k_proj, [2d,3d) = v_proj (three separate GEMMs in attention.rs:912-914)
+    if (quant) {
+      // dequant-in-prologue: upload the packed bytes as they are; every layer shares one set of bf16 expansion buffers
+      const size_t qb = f.cfg.quantization == 2 ? d * d : d * d / 2;        // bytes of one d x d tensor (d is even)
+      if ((rc = dev_alloc(m, 3 * qb, &w.pqkv)) != WB_OK || (rc = dev_alloc(m, qb, &w.po)) != WB_OK ||
+          (rc = dev_alloc(m, 4 * qb, &w.p1)) != WB_OK || (rc = dev_alloc(m, 4 * qb, &w.p2)) != WB_OK)
+        return done(rc);
+      WB_CUDA_OK(cudaMemsetAsync(w.pqkv, 0, 3 * qb, m->stream));
+      WB_CUDA_OK(cudaMemsetAsync(w.po, 0, qb, m->stream));
+      WB_CUDA_OK(cudaMemsetAsync(w.p1, 0, 4 * qb, m->stream));
+      WB_CUDA_OK(cudaMemsetAsync(w.p2, 0, 4 * qb, m->stream));
+      w.wqkv = m->xp_qkv; w.wo = m->xp_o; w.w1 = m->xp_1; w.w2 = m->xp_2;
+      if ((rc = dev_alloc(m, 3 * d, &w.bqkv)) != WB_OK) return done(rc);
+      if ((rc = fill_f32(m, w.bqkv, 3 * d, 0.f)) != WB_OK) return done(rc);
+      float sc[3] = {1.f, 1.f, 1.f};
+      const char* proj[3] = {".self_attn.q_proj", ".self_attn.k_proj", ".self_attn.v_proj"};
+      for (int k = 0; k < 3; ++k) {
+        if ((rc = up.load_packed(p + proj[k] + ".weight", w.pqkv + k * qb, d * d, &sc[k])) != WB_OK) return done(rc);
+        if ((rc = up.load_f32(p + proj[k] + ".bias", w.bqkv + k * d, d)) != WB_OK) return done(rc);
+      }
+      if ((rc = dev_alloc(m, 3 * d, &w.sqkv)) != WB_OK) return done(rc);
+      std::vector<float> h(3 * d);
+      for (int k = 0; k < 3; ++k) std::fill(h.begin() + k * d, h.begin() + (k + 1) * d, sc[k]);
+      WB_CUDA_OK(cudaMemcpy(w.sqkv, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+      if ((rc = up.load_packed(p + ".self_attn.out_proj.weight", w.po, d * d, &w.so)) != WB_OK) return done(rc);
+      if ((rc = new_f32_param(m, up, p + ".self_attn.out_proj.bias", d, 0.f, &w.bo)) != WB_OK) return done(rc);
+      if ((rc = up.load_packed(p + ".fc1.weight", w.p1, 4 * d * d, &w.s1)) != WB_OK) return done(rc);
+      if ((rc = new_f32_param(m, up, p + ".fc1.bias", 4 * d, 0.f, &w.b1)) != WB_OK) return done(rc);
+      if ((rc = up.load_packed(p + ".fc2.weight", w.p2, 4 * d * d, &w.s2)) != WB_OK) return done(rc);
+      if ((rc = new_f32_param(m, up, p + ".fc2.bias", d, 0.f, &w.b2)) != WB_OK) return done(rc);
+      continue;
+    }
     if ((rc = dev_alloc(m, 3 * d * d, &w.wqkv)) != WB_OK) return done(rc);
     WB_CUDA_OK(cudaMemset(w.wqkv, 0, 3 * d * d * sizeof(bf16)));
     if ((rc = dev_alloc(m, 3 * d, &w.bqkv)) != WB_OK) return done(rc);
@@ -408,14 +465,26 @@ int encode_device(wb_model* m, int B, int T, void* d_out, wb_dtype out_dtype, in
     q.out = out; q.ldc = N; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
     return launch_gemm(q, st);
   };
+  // Quantised models: a layer's packed weights are expanded to bf16 (exact integer values; the scale stays in the GEMM epilogue)
+  // right before the GEMM that consumes them, into buffers every layer reuses.  With M = B x 1500 rows per launch each weight tile
+  // is consumed by ~190 row tiles, so expanding once per launch costs 1/190th of converting inside every CTA, and the 12 d^2
+  // bf16 (39 MB for d = 1280) stay L2-resident for the GEMM that follows; HBM only ever holds the packed bytes.
+  const size_t dd = static_cast<size_t>(d) * d;
+  auto expand = [&](const uint8_t* packed, bf16* dst, size_t n) {
+    return m->quant == 2 ? launch_i8_to_bf16(reinterpret_cast<const int8_t*>(packed), dst, n, st) : launch_i4_to_bf16(packed, dst, n, st);
+  };
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = m->layers[i];
     WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, nullptr, st));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.pqkv, lw.wqkv, 3 * dd)); }
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p));
     WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.po, lw.wo, dd)); }
     WB_PROF(PC_GEMM, flat(w.att.p, d, lw.wo, d, EPI_RESID_F32, lw.so, nullptr, lw.bo, w.x.p));
     WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln2_g, lw.ln2_b, M, d, w.xn.p, nullptr, st));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p1, lw.w1, 4 * dd)); }
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.w1, 4 * d, EPI_GELU_BF16, lw.s1, nullptr, lw.b1, w.hid.p));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p2, lw.w2, 4 * dd)); }
     WB_PROF(PC_GEMM, flat(w.hid.p, 4 * d, lw.w2, d, EPI_RESID_F32, lw.s2, nullptr, lw.b2, w.x.p));
   }
   if (ln_post) {
