@@ -297,8 +297,17 @@ def main():
     mel_ms = (prof["mel_stft"]["ms"] + prof["mel_finalize"]["ms"]) / PSTEPS
     ln_ms = prof["layernorm"]["ms"] / PSTEPS
     step_ms = ms / args.steps
-    roofline = {"kernel": "gemm_tn_kernel (tcgen05)", "bound": "tensor", "achieved": gemm_flops / (g_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": gemm_flops / (g_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
+    traffic = None                      # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if args.model == "large-v3" and B == 32:
+            traffic = tr["dram_bytes_per_launch_mean"]
+    except Exception:
+        pass
+    roofline = {"kernel": "gemm2_tn_kernel (tcgen05, cta_group::2)", "bound": "tensor", "achieved": gemm_flops / (g_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": gemm_flops / (g_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                # operands once + outputs (bf16 activations, f32 residual read-modify-write), mean over the 4 GEMMs of a layer
+                "algorithmic_bytes_per_launch": (44 * B * S * d + 24 * d * d) / 4 if traffic else None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": prof["gemm"]["launches"] // PSTEPS, "ms_per_step": g_ms, "share_of_step": g_ms / step_ms}
     kernels = {
