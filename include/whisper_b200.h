@@ -117,6 +117,12 @@ int wb_encode_batch(const wb_model* m, const float* const* mels, const size_t* m
  * This is the measured entry point (bench.py `e2e`): host buffers in, host buffer out. */
 int wb_mel_encode_batch(const wb_model* m, const float* const* audio, const size_t* n_samples, int B, void* out,
                         wb_dtype out_dtype);
+/* The same call without the final wait: host->device copies, compute and the device->host copy of the result are enqueued
+ * on three streams (copy-in, the model's stream, copy-out) over two staging slots, so the copies of one batch overlap the
+ * compute of its neighbours; a third call blocks until the oldest batch has left its slot.  `audio[i]` and `out` must
+ * stay valid (and should be pinned) until wb_sync returns; results are complete after wb_sync. */
+int wb_mel_encode_batch_async(const wb_model* m, const float* const* audio, const size_t* n_samples, int B, void* out,
+                              wb_dtype out_dtype);
 /* Same work with inputs already resident in HBM: d_audio [B][480000] f32 (device), d_out
  * [B][1500][d] (device).  Enqueues on the model's stream; does not synchronise. */
 int wb_mel_encode_batch_dev(const wb_model* m, const float* d_audio, int B, void* d_out, wb_dtype out_dtype);

@@ -304,3 +304,38 @@ def test_full_size_properties_large_v3_shape():
     perm = model.mel_encode_batch([audio[3], audio[0]])
     assert np.array_equal(perm[0], out[3]) and np.array_equal(perm[1], out[0])   # chunks are independent units
     model.close()
+
+
+@pytest.mark.gpu
+def test_async_pipeline_matches_sync(tiny):
+    """wb_mel_encode_batch_async over both staging slots (4 calls in flight) returns what the synchronous call returns."""
+    model, _, _ = tiny
+    d = model.config.n_audio_state
+    batches = [[synth.synth_audio(10 * k + i)[: 480000 - 1000 * i].copy() for i in range(2)] for k in range(4)]
+    want = [model.mel_encode_batch(b) for b in batches]
+    outs = [np.zeros((2, 1500, d), np.float32) for _ in range(4)]
+    for b, o in zip(batches, outs):
+        model.mel_encode_batch_async(b, o)
+    model.sync()
+    for w, o in zip(want, outs):
+        assert np.array_equal(w, o)
+
+
+@pytest.mark.gpu
+def test_streaming_chunks_int4(fb80):
+    """BASELINE config 5 at test size: a long stream cut by split_into_chunks(5 s, 0.5 s overlap) (batch.rs:219-240), every chunk
+    zero-padded to 30 s by compute_mel (lib.rs:413-420), int4 `.apr` payload, through the fused batch entry point."""
+    cfg = synth.CONFIGS["tiny"]
+    data, _ = synth.random_model_apr(cfg, quant=F.Q_INT4, seed=0)
+    w = F.AprReader(data).load_all()
+    model = WhisperApr.load_from_apr(data)
+    stream = np.concatenate([synth.synth_audio(40), synth.synth_audio(41)])[:200000]
+    from whisper_apr_b200 import api
+    chunks = api.split_into_chunks(stream, 80000, 8000)
+    assert [c.size for c in chunks] == [80000, 80000, 56000]
+    assert np.array_equal(chunks[1], stream[72000:152000]) and np.array_equal(chunks[2], stream[144000:])
+    out = model.mel_encode_batch(chunks)
+    for i, c in enumerate(chunks):
+        ref = E.forward_mel(M.compute_mel(c, fb80), w, E.CONFIGS["tiny"], attention=E.naive_attention)
+        assert np.abs(out[i] - ref).max() <= ENC_TOL and _cos(out[i], ref) >= ENC_COS
+    model.close()

@@ -196,6 +196,13 @@ class WhisperApr:
         check(_lib.lib().wb_mel_encode_batch(self._h, ptrs, lens, B, _ptr(out), code))
         return out
 
+    def mel_encode_batch_async(self, audio_batch, out: np.ndarray, out_dtype: str = "f32"):
+        """Enqueue form of mel_encode_batch: `audio_batch` (contiguous f32 arrays) and `out` must stay alive until sync()."""
+        B = len(audio_batch)
+        ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in audio_batch])
+        lens = (C.c_size_t * B)(*[a.size for a in audio_batch])
+        check(_lib.lib().wb_mel_encode_batch_async(self._h, ptrs, lens, B, _ptr(out), WB_F32 if out_dtype == "f32" else WB_BF16))
+
     # -- device-pointer entry points (inputs already in HBM) ------------------------------
     def mel_encode_batch_dev(self, d_audio_ptr: int, B: int, d_out_ptr: int, out_dtype: str = "f32"):
         check(_lib.lib().wb_mel_encode_batch_dev(self._h, C.c_void_p(d_audio_ptr), B, C.c_void_p(d_out_ptr),

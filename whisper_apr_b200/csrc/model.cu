@@ -97,6 +97,18 @@ struct wb_model {
   wb::bf16 *xp_qkv = nullptr, *xp_o = nullptr, *xp_1 = nullptr, *xp_2 = nullptr;   // expansion buffers (12 d^2 bf16: L2-sized)
   float *lnp_g = nullptr, *lnp_b = nullptr;
   wb::Workspace ws;
+  // copy/compute overlap of the host-buffer entry point: two staging slots, copy-in and copy-out streams
+  struct Slot {
+    wb::DevBuf<float> audio;
+    wb::DevBuf<int> n_valid;
+    wb::DevBuf<uint8_t> out;
+    int* h_n_valid = nullptr;          // pinned
+    int h_cap = 0;
+    cudaEvent_t in_done = nullptr, compute_done = nullptr, out_done = nullptr;
+    bool busy = false;
+  } slot[2];
+  int next_slot = 0;
+  cudaStream_t in_stream = nullptr, out_stream = nullptr;
   // per-kernel timing (wb_profile_*): CUDA events recorded on the launching stream around every launch
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;      // start/stop pairs
@@ -602,6 +614,15 @@ void wb_model_free(wb_model* m) {
   w.audio.release(); w.logmel.release(); w.mel_f32.release(); w.x.release(); w.out_f32.release();
   w.n_valid.release(); w.max_key.release();
   w.mel_bf16.release(); w.c1.release(); w.xn.release(); w.qkv.release(); w.att.release(); w.hid.release(); w.out_bf16.release();
+  for (auto& sl : m->slot) {
+    sl.audio.release(); sl.n_valid.release(); sl.out.release();
+    if (sl.h_n_valid) cudaFreeHost(sl.h_n_valid);
+    if (sl.in_done) cudaEventDestroy(sl.in_done);
+    if (sl.compute_done) cudaEventDestroy(sl.compute_done);
+    if (sl.out_done) cudaEventDestroy(sl.out_done);
+  }
+  if (m->in_stream) cudaStreamDestroy(m->in_stream);
+  if (m->out_stream) cudaStreamDestroy(m->out_stream);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
 }
@@ -623,7 +644,14 @@ int wb_model_set_max_batch(wb_model* m, int max_chunks) {
 int wb_sync(const wb_model* cm) {
   wb_model* m = const_cast<wb_model*>(cm);
   if (!m) return set_error(WB_ERR_MODEL, "null model");
+  std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
+  for (auto& sl : m->slot) {
+    if (sl.busy) {
+      WB_CUDA_OK(cudaEventSynchronize(sl.out_done));
+      sl.busy = false;
+    }
+  }
   WB_CUDA_OK(cudaStreamSynchronize(m->stream));
   return WB_OK;
 }
@@ -851,33 +879,78 @@ int wb_mel_encode_batch_dev(const wb_model* cm, const float* d_audio, int B, voi
   return WB_OK;
 }
 
-int wb_mel_encode_batch(const wb_model* cm, const float* const* audio, const size_t* n_samples, int B, void* out, wb_dtype out_dtype) {
+static int prepare_slot(wb_model* m, wb_model::Slot& sl, int nb, size_t out_bytes) {
+  int rc;
+  if (!m->in_stream) {
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
+  }
+  if (!sl.in_done) {
+    WB_CUDA_OK(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+    WB_CUDA_OK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+    WB_CUDA_OK(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+  }
+  if (sl.busy) {                                         // the batch that used this slot two calls ago must have left it
+    WB_CUDA_OK(cudaEventSynchronize(sl.out_done));
+    sl.busy = false;
+  }
+  if ((rc = sl.audio.ensure(static_cast<size_t>(nb) * N_SAMPLES_30S)) != WB_OK) return rc;
+  if ((rc = sl.n_valid.ensure(nb)) != WB_OK) return rc;
+  if ((rc = sl.out.ensure(out_bytes)) != WB_OK) return rc;
+  if (sl.h_cap < nb) {
+    if (sl.h_n_valid) cudaFreeHost(sl.h_n_valid);
+    sl.h_n_valid = nullptr;
+    WB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&sl.h_n_valid), static_cast<size_t>(nb) * sizeof(int), cudaHostAllocDefault));
+    sl.h_cap = nb;
+  }
+  return WB_OK;
+}
+
+// transcribe_batch_optimized steps 1-2 from host buffers.  Per micro-batch: copy-in stream (audio H2D) -> the model's stream (mel +
+// encoder) -> copy-out stream (states D2H), chained by events over two staging slots.
+static int mel_encode_batch_enqueue(wb_model* m, const float* const* audio, const size_t* n_samples, int B, void* out, wb_dtype out_dtype) {
+  int rc;
+  const size_t d = m->cfg.n_audio_state, S = (N_FRAMES_30S - 1) / 2 + 1, esz = out_dtype == WB_BF16 ? 2 : 4;
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = std::min(m->max_batch, B - b0);
+    const size_t out_bytes = static_cast<size_t>(nb) * S * d * esz;
+    wb_model::Slot& sl = m->slot[m->next_slot];
+    m->next_slot ^= 1;
+    if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
+    if ((rc = prepare_slot(m, sl, nb, out_bytes)) != WB_OK) return rc;
+    for (int i = 0; i < nb; ++i) {
+      const size_t n = std::min<size_t>(n_samples[b0 + i], N_SAMPLES_30S);
+      sl.h_n_valid[i] = static_cast<int>(n);
+      if (n) WB_CUDA_OK(cudaMemcpyAsync(sl.audio.p + static_cast<size_t>(i) * N_SAMPLES_30S, audio[b0 + i], n * 4, cudaMemcpyHostToDevice, m->in_stream));
+    }
+    WB_CUDA_OK(cudaMemcpyAsync(sl.n_valid.p, sl.h_n_valid, nb * sizeof(int), cudaMemcpyHostToDevice, m->in_stream));
+    WB_CUDA_OK(cudaEventRecord(sl.in_done, m->in_stream));
+    WB_CUDA_OK(cudaStreamWaitEvent(m->stream, sl.in_done, 0));
+    if ((rc = mel_device(m, sl.audio.p, sl.n_valid.p, nb, nullptr, true)) != WB_OK) return rc;
+    if ((rc = encode_device(m, nb, N_FRAMES_30S, sl.out.p, out_dtype, -1, true)) != WB_OK) return rc;
+    WB_CUDA_OK(cudaEventRecord(sl.compute_done, m->stream));
+    WB_CUDA_OK(cudaStreamWaitEvent(m->out_stream, sl.compute_done, 0));
+    WB_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(out) + static_cast<size_t>(b0) * S * d * esz, sl.out.p, out_bytes, cudaMemcpyDeviceToHost, m->out_stream));
+    WB_CUDA_OK(cudaEventRecord(sl.out_done, m->out_stream));
+    sl.busy = true;
+  }
+  return WB_OK;
+}
+
+int wb_mel_encode_batch_async(const wb_model* cm, const float* const* audio, const size_t* n_samples, int B, void* out, wb_dtype out_dtype) {
   wb_model* m = const_cast<wb_model*>(cm);
   if (!m || !audio || !n_samples || !out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
   int rc = check_encoder_dims(m);
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
-  const size_t d = m->cfg.n_audio_state, S = (N_FRAMES_30S - 1) / 2 + 1, esz = out_dtype == WB_BF16 ? 2 : 4;
-  std::vector<int> nv;
-  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
-    const int nb = std::min(m->max_batch, B - b0);
-    if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
-    nv.assign(nb, 0);
-    for (int i = 0; i < nb; ++i) {
-      const size_t n = std::min<size_t>(n_samples[b0 + i], N_SAMPLES_30S);
-      nv[i] = static_cast<int>(n);
-      if (n) WB_CUDA_OK(cudaMemcpyAsync(m->ws.audio.p + static_cast<size_t>(i) * N_SAMPLES_30S, audio[b0 + i], n * 4, cudaMemcpyHostToDevice, m->stream));
-    }
-    WB_CUDA_OK(cudaMemcpyAsync(m->ws.n_valid.p, nv.data(), nb * sizeof(int), cudaMemcpyHostToDevice, m->stream));
-    if ((rc = mel_device(m, m->ws.audio.p, m->ws.n_valid.p, nb, nullptr, true)) != WB_OK) return rc;
-    void* dst_dev = out_dtype == WB_BF16 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
-    if ((rc = encode_device(m, nb, N_FRAMES_30S, dst_dev, out_dtype, -1, true)) != WB_OK) return rc;
-    WB_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(out) + static_cast<size_t>(b0) * S * d * esz, dst_dev, static_cast<size_t>(nb) * S * d * esz,
-                               cudaMemcpyDeviceToHost, m->stream));
-    WB_CUDA_OK(cudaStreamSynchronize(m->stream));
-  }
-  return WB_OK;
+  return mel_encode_batch_enqueue(m, audio, n_samples, B, out, out_dtype);
+}
+
+int wb_mel_encode_batch(const wb_model* cm, const float* const* audio, const size_t* n_samples, int B, void* out, wb_dtype out_dtype) {
+  int rc = wb_mel_encode_batch_async(cm, audio, n_samples, B, out, out_dtype);
+  if (rc != WB_OK) return rc;
+  return wb_sync(cm);
 }
 
 // ------------------------------------------------------------------------------------------ chunking
