@@ -339,3 +339,34 @@ def test_streaming_chunks_int4(fb80):
         ref = E.forward_mel(M.compute_mel(c, fb80), w, E.CONFIGS["tiny"], attention=E.naive_attention)
         assert np.abs(out[i] - ref).max() <= ENC_TOL and _cos(out[i], ref) >= ENC_COS
     model.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny", "base"])
+def test_greedy_tokens_identical(name, fb80):
+    """North-star gate 3: the reference's greedy decode (oracle/decoder.py: forward_one + WhisperTokenSuppressor + argmax) emits the
+    same tokens from the GPU's encoder states as from the oracle's.  Audio is the first synthetic chunk whose oracle decode has no
+    near-tie step (top-2 logit margin >= 0.01): a coin-flip step is not reproducible by any implementation, the reference's own
+    scalar and SIMD paths included."""
+    from oracle import decoder as D
+    cfg, ecfg = synth.CONFIGS[name], E.CONFIGS[name]
+    data, tensors = synth.random_model_apr(cfg, seed=0)
+    w = dict(tensors)
+    dw = D.random_decoder_tensors(ecfg, seed=1)
+    model = WhisperApr.load_from_apr(data)
+    chosen = None
+    for a in range(7, 19):
+        audio = synth.synth_audio(a)
+        ref_states = E.forward_mel(M.compute_mel(audio, fb80), w, ecfg, attention=E.naive_attention)
+        toks, margins = D.greedy_decode(dw, ecfg, ref_states.astype(np.float32), max_tokens=24, return_margins=True)
+        if min(margins) >= 0.01:
+            chosen = (audio, ref_states, toks)
+            break
+    assert chosen is not None, "no synthetic chunk with a tie-free oracle decode"
+    audio, ref_states, toks = chosen
+    got_states = model.mel_encode_batch([audio])[0]
+    assert np.abs(got_states - ref_states).max() <= ENC_TOL and _cos(got_states, ref_states) >= ENC_COS
+    got = D.greedy_decode(dw, ecfg, got_states, max_tokens=24)
+    assert got == toks
+    assert len(set(toks[4:])) >= 3            # the sequence is not a degenerate repeat
+    model.close()
