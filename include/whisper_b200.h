@@ -137,6 +137,12 @@ int wb_sync(const wb_model* m);
  * pairs; returns the number of chunks the reference would produce (may exceed capacity). */
 size_t wb_split_into_chunks(size_t n_samples, size_t chunk_size, size_t overlap, size_t* starts, size_t* lens,
                             size_t capacity);
+/* BatchPreprocessor::process_batch (src/audio/batch.rs:157-176): segment i (n_samples[i] samples, any length) ->
+ * mels_out[i] = MelFilterbank::compute(segment, hop) with the preprocessor's own HTK filterbank MelFilterbank::new(n_mels, 400,
+ * 16000) (batch.rs:143) -- not the model's -- no 30 s padding; frame_counts[i] frames of n_mels values, *max_frames_out as
+ * BatchMelResult::max_frames.  out_capacity[i] in floats.  AudioConfig::default(): n_mels 80, hop 160. */
+int wb_batch_preprocess(const wb_model* m, const float* const* audio, const size_t* n_samples, int B, size_t n_mels, size_t hop,
+                        float* const* mels_out, const size_t* out_capacity, size_t* frame_counts, size_t* max_frames_out);
 /* BatchMelResult::to_padded_tensor (src/audio/batch.rs:107-127): [B][n_mels][max_frames], zero padded. */
 int wb_to_padded_tensor(const float* const* mels, const size_t* frame_counts, int B, size_t n_mels, size_t max_frames,
                         float* out);

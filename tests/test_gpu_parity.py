@@ -370,3 +370,31 @@ def test_greedy_tokens_identical(name, fb80):
     assert got == toks
     assert len(set(toks[4:])) >= 3            # the sequence is not a degenerate repeat
     model.close()
+
+
+@pytest.mark.gpu
+def test_batch_preprocessor_ragged_htk(tiny):
+    """BatchPreprocessor::process_batch (batch.rs:157-176): ragged segments, the preprocessor's own HTK filterbank (batch.rs:143),
+    no padding; BatchMelResult bookkeeping and to_padded_tensor (batch.rs:107-127); the reference's own edge cases (empty / short)."""
+    from whisper_apr_b200 import AudioBatch, BatchPreprocessor
+    model, _, _ = tiny
+    batch = AudioBatch()
+    lens = [16000, 24000, 399, 0, 400, 5000]
+    for i, n in enumerate(lens):
+        batch.add_segment(synth.synth_audio(30 + i)[:n])
+    res = BatchPreprocessor(model).process_batch(batch)
+    assert res.frame_counts == [98, 148, 0, 0, 1, 29] and res.max_frames == 148 and len(res) == 6     # mel.rs:660-668 frame-count KATs
+    fb = M.htk_filterbank(80)
+    for seg, mel in zip(batch.segments, res.mels):
+        ref = M.mel_compute(seg, fb)
+        assert mel.shape == ref.shape
+        if ref.size:
+            assert np.abs(mel - ref).max() <= MEL_TOL
+    padded = res.to_padded_tensor()
+    assert padded.shape == (6, 80, 148)
+    assert np.array_equal(padded, M.to_padded_tensor(res.mels, 80))
+    norm = BatchPreprocessor.normalize_batch(batch)
+    assert abs(float(np.abs(norm.segments[0]).max()) - 1.0) < 1e-6 and norm.segments[3].size == 0
+    # a 128-mel preprocessor on the same model handle (tables are per n_mels)
+    res128 = BatchPreprocessor(model, n_mels=128).process_batch(batch)
+    assert np.abs(res128.mels[1] - M.mel_compute(batch.segments[1], M.htk_filterbank(128))).max() <= MEL_TOL

@@ -9,8 +9,8 @@ Only what the path needs lives here: ``csrc/`` (hand-written CUDA kernels + the 
 synthetic workload generator.
 """
 from ._lib import LIB_PATH, WhisperError, build, lib  # noqa: F401
-from .api import (BatchEncoderOutput, WhisperApr, bf16_bits_to_f32, split_into_chunks,  # noqa: F401
-                  to_padded_tensor)
+from .api import (AudioBatch, BatchEncoderOutput, BatchMelResult, BatchPreprocessor, WhisperApr, bf16_bits_to_f32,  # noqa: F401
+                  split_into_chunks, to_padded_tensor)
 
-__all__ = ["WhisperApr", "WhisperError", "BatchEncoderOutput", "split_into_chunks", "to_padded_tensor",
-           "bf16_bits_to_f32", "build", "lib", "LIB_PATH"]
+__all__ = ["WhisperApr", "WhisperError", "BatchEncoderOutput", "AudioBatch", "BatchPreprocessor", "BatchMelResult",
+           "split_into_chunks", "to_padded_tensor", "bf16_bits_to_f32", "build", "lib", "LIB_PATH"]

@@ -43,6 +43,7 @@ SIGNATURES = {
     "wb_encode": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp]),
     "wb_encode_batch": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, _vp, C.c_size_t, _szp, _szp]),
     "wb_mel_encode_batch": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, _vp, C.c_int]),
+    "wb_batch_preprocess": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, C.c_size_t, C.c_size_t, C.POINTER(_vp), _szp, _szp, _szp]),
     "wb_mel_encode_batch_async": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, _vp, C.c_int]),
     "wb_mel_encode_batch_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int]),
     "wb_compute_mel_batch_dev": (C.c_int, [_vp, _vp, C.c_int, _vp]),

@@ -239,6 +239,68 @@ class WhisperApr:
         return out
 
 
+class AudioBatch:
+    """audio::AudioBatch (src/audio/batch.rs:10-70): an ordered list of segments of any length."""
+
+    def __init__(self, n_mels: int = 80, hop_length: int = HOP_LENGTH):
+        self.n_mels, self.hop_length = n_mels, hop_length          # AudioConfig::default (src/audio/mod.rs:30-61)
+        self.segments: list[np.ndarray] = []
+
+    def add_segment(self, samples):
+        self.segments.append(_f32(samples).ravel().copy())
+
+    def __len__(self):
+        return len(self.segments)
+
+    def is_empty(self) -> bool:
+        return not self.segments
+
+
+class BatchMelResult:
+    """audio::BatchMelResult (src/audio/batch.rs:72-127)."""
+
+    def __init__(self, mels, frame_counts, max_frames, n_mels):
+        self.mels, self.frame_counts, self.max_frames, self.n_mels = mels, frame_counts, max_frames, n_mels
+
+    def __len__(self):
+        return len(self.mels)
+
+    def to_padded_tensor(self) -> np.ndarray:
+        return to_padded_tensor(self.mels, self.n_mels)
+
+
+class BatchPreprocessor:
+    """audio::BatchPreprocessor (src/audio/batch.rs:129-205): per-segment mel with the preprocessor's own HTK filterbank
+    (MelFilterbank::new, batch.rs:143), no 30 s padding.  Runs on the model's device."""
+
+    def __init__(self, model: "WhisperApr", n_mels: int = 80, hop_length: int = HOP_LENGTH):
+        self._model, self.n_mels, self.hop_length = model, n_mels, hop_length
+
+    def process_batch(self, batch: AudioBatch) -> BatchMelResult:
+        B = len(batch)
+        caps = [max(0, (s.size - N_FFT) // self.hop_length + 1 if s.size >= N_FFT else 0) * self.n_mels for s in batch.segments]
+        outs = [np.empty(max(c, 1), np.float32) for c in caps]
+        counts = (C.c_size_t * max(B, 1))()
+        max_frames = C.c_size_t(0)
+        if B:
+            ptrs = (C.c_void_p * B)(*[s.ctypes.data for s in batch.segments])
+            lens = (C.c_size_t * B)(*[s.size for s in batch.segments])
+            optrs = (C.c_void_p * B)(*[o.ctypes.data for o in outs])
+            ocap = (C.c_size_t * B)(*caps)
+            check(_lib.lib().wb_batch_preprocess(self._model._h, ptrs, lens, B, self.n_mels, self.hop_length, optrs, ocap, counts, C.byref(max_frames)))
+        mels = [o[: counts[i] * self.n_mels].reshape(counts[i], self.n_mels) for i, o in enumerate(outs)]
+        return BatchMelResult(mels, [int(counts[i]) for i in range(B)], int(max_frames.value), self.n_mels)
+
+    @staticmethod
+    def normalize_batch(batch: AudioBatch) -> AudioBatch:
+        """normalize_audio per segment (batch.rs:179-215): divide by max |x| unless it is below f32 epsilon."""
+        out = AudioBatch(batch.n_mels, batch.hop_length)
+        for s in batch.segments:
+            m = float(np.abs(s).max()) if s.size else 0.0
+            out.add_segment(s if m < np.finfo(np.float32).eps else (s / np.float32(m)).astype(np.float32))
+        return out
+
+
 def split_into_chunks(samples, chunk_size: int, overlap: int):
     """audio::split_into_chunks (src/audio/batch.rs:219-240)."""
     samples = _f32(samples).ravel()

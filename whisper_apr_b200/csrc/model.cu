@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -87,6 +88,7 @@ struct wb_model {
   std::vector<void*> allocs;            // weight allocations (freed in wb_model_free)
   // mel
   wb::MelTables mel{};
+  std::map<int, wb::MelTables> htk_tables;   // BatchPreprocessor filterbanks by n_mels (built on first use)
   // conv stem
   wb::bf16 *conv1_w = nullptr, *conv2_w = nullptr;
   float *conv1_b = nullptr, *conv2_b = nullptr;
@@ -257,18 +259,8 @@ int new_weight(wb_model* m, Uploader& up, const std::string& name, size_t count,
   return up.load_bf16(name, *out, count, scale);
 }
 
-int build_mel_tables(wb_model* m, const AprFile& f) {
-  std::vector<float> filt;
-  int n_mels = static_cast<int>(m->cfg.n_mels);
-  if (f.has_filterbank && f.fb_freqs == N_FREQ && f.fb_mels > 0) {
-    // lib.rs:738-741: the embedded (slaney) filterbank defines n_mels of the mel stage
-    n_mels = static_cast<int>(f.fb_mels);
-    filt.resize(static_cast<size_t>(n_mels) * N_FREQ);
-    memcpy(filt.data(), f.fb_data, filt.size() * 4);
-  } else {
-    if (n_mels <= 0) return set_error(WB_ERR_FORMAT, "model has no mel filterbank and n_mels == 0");
-    filt = htk_filterbank(n_mels, N_FFT, 16000);          // lib.rs:297-298 -> MelFilterbank::new
-  }
+// filters [n_mels][201] -> device tables (dense rows + the first/last non-zero bin of every row + the periodic Hann window)
+int upload_mel_tables(wb_model* m, const std::vector<float>& filt, int n_mels, MelTables* out) {
   std::vector<int> lo(n_mels, 0), len(n_mels, 0);
   for (int j = 0; j < n_mels; ++j) {
     int first = -1, last = -1;
@@ -291,12 +283,27 @@ int build_mel_tables(wb_model* m, const AprFile& f) {
   WB_CUDA_OK(cudaMemcpy(d_filt, filt.data(), filt.size() * 4, cudaMemcpyHostToDevice));
   WB_CUDA_OK(cudaMemcpy(d_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
   WB_CUDA_OK(cudaMemcpy(d_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice));
-  m->mel.window = d_win;
-  m->mel.filters = d_filt;
-  m->mel.span_lo = d_lo;
-  m->mel.span_len = d_len;
-  m->mel.n_mels = n_mels;
+  out->window = d_win;
+  out->filters = d_filt;
+  out->span_lo = d_lo;
+  out->span_len = d_len;
+  out->n_mels = n_mels;
   return WB_OK;
+}
+
+int build_mel_tables(wb_model* m, const AprFile& f) {
+  std::vector<float> filt;
+  int n_mels = static_cast<int>(m->cfg.n_mels);
+  if (f.has_filterbank && f.fb_freqs == N_FREQ && f.fb_mels > 0) {
+    // lib.rs:738-741: the embedded (slaney) filterbank defines n_mels of the mel stage
+    n_mels = static_cast<int>(f.fb_mels);
+    filt.resize(static_cast<size_t>(n_mels) * N_FREQ);
+    memcpy(filt.data(), f.fb_data, filt.size() * 4);
+  } else {
+    if (n_mels <= 0) return set_error(WB_ERR_FORMAT, "model has no mel filterbank and n_mels == 0");
+    filt = htk_filterbank(n_mels, N_FFT, 16000);          // lib.rs:297-298 -> MelFilterbank::new
+  }
+  return upload_mel_tables(m, filt, n_mels, &m->mel);
 }
 
 int load_weights(wb_model* m, const AprFile& f) {
@@ -657,20 +664,17 @@ int wb_sync(const wb_model* cm) {
 }
 
 // ---------------------------------------------------------------------------------------------- mel
-int wb_mel_compute(const wb_model* cm, const float* audio, size_t n, size_t hop, float* out, size_t out_capacity,
-                   size_t* n_frames_out) {
-  wb_model* m = const_cast<wb_model*>(cm);
-  if (!m) return set_error(WB_ERR_MODEL, "null model");
+// MelFilterbank::compute for one segment with the given filter tables (host in, host out).  Caller holds the model lock.
+static int mel_compute_one(wb_model* m, const MelTables& tab, const float* audio, size_t n, size_t hop, float* out, size_t out_capacity,
+                           size_t* n_frames_out) {
   if (n_frames_out) *n_frames_out = 0;
   if (n == 0) return WB_OK;                                                        // mel.rs:236-238
   if (hop == 0) return set_error(WB_ERR_AUDIO, "hop_length must be positive");     // mel.rs:240-242
   const size_t n_frames = n >= N_FFT ? (n - N_FFT) / hop + 1 : 0;                  // mel.rs:245-249
   if (n_frames == 0) return WB_OK;
-  const int nm = m->mel.n_mels;
+  const int nm = tab.n_mels;
   if (n > 0x7fff0000ull || hop > 0x7fff0000ull) return set_error(WB_ERR_AUDIO, "audio too long for one call");
   if (!audio || !out || out_capacity < n_frames * nm) return set_error(WB_ERR_AUDIO, "output buffer too small");
-  std::lock_guard<std::mutex> lk(m->mu);
-  DeviceGuard guard(m->device);
   DevBuf<float> d_audio, d_log, d_out;
   DevBuf<int> d_key;
   int rc;
@@ -682,7 +686,7 @@ int wb_mel_compute(const wb_model* cm, const float* audio, size_t n, size_t hop,
   if (cudaMemcpyAsync(d_audio.p, audio, n * 4, cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
     return cleanup(set_error(WB_ERR_CUDA, "H2D audio copy failed"));
   rc = launch_mel_stft(d_audio.p, static_cast<long long>(d_audio.n), nullptr, static_cast<int>(n), static_cast<int>(hop),
-                       static_cast<int>(n_frames), 1, m->mel, d_log.p, d_key.p, m->stream);
+                       static_cast<int>(n_frames), 1, tab, d_log.p, d_key.p, m->stream);
   if (rc != WB_OK) return cleanup(rc);
   rc = launch_mel_finalize(d_log.p, d_key.p, static_cast<int>(n_frames), static_cast<int>(n_frames), nm, 1, d_out.p, nullptr, m->stream);
   if (rc != WB_OK) return cleanup(rc);
@@ -691,6 +695,47 @@ int wb_mel_compute(const wb_model* cm, const float* audio, size_t n, size_t hop,
     return cleanup(set_error(WB_ERR_CUDA, std::string("mel kernels failed: ") + cudaGetErrorString(cudaGetLastError())));
   if (n_frames_out) *n_frames_out = n_frames;
   return cleanup(WB_OK);
+}
+
+int wb_mel_compute(const wb_model* cm, const float* audio, size_t n, size_t hop, float* out, size_t out_capacity,
+                   size_t* n_frames_out) {
+  wb_model* m = const_cast<wb_model*>(cm);
+  if (!m) return set_error(WB_ERR_MODEL, "null model");
+  std::lock_guard<std::mutex> lk(m->mu);
+  DeviceGuard guard(m->device);
+  return mel_compute_one(m, m->mel, audio, n, hop, out, out_capacity, n_frames_out);
+}
+
+// BatchPreprocessor::process_batch (src/audio/batch.rs:157-176): every segment goes through MelFilterbank::compute with the
+// preprocessor's OWN filterbank -- MelFilterbank::new(n_mels, n_fft, sample_rate), the HTK triangles (batch.rs:143), not the model's --
+// and is neither padded nor truncated.  Tables for a given n_mels are built once per model and kept.
+int wb_batch_preprocess(const wb_model* cm, const float* const* audio, const size_t* n_samples, int B, size_t n_mels, size_t hop,
+                        float* const* mels_out, const size_t* out_capacity, size_t* frame_counts, size_t* max_frames_out) {
+  wb_model* m = const_cast<wb_model*>(cm);
+  if (!m) return set_error(WB_ERR_MODEL, "null model");
+  if (B < 0 || (B > 0 && (!audio || !n_samples || !mels_out || !out_capacity || !frame_counts)))
+    return set_error(WB_ERR_AUDIO, "null argument");
+  if (n_mels == 0 || n_mels > 1024) return set_error(WB_ERR_AUDIO, "n_mels out of range");
+  if (max_frames_out) *max_frames_out = 0;
+  std::lock_guard<std::mutex> lk(m->mu);
+  DeviceGuard guard(m->device);
+  auto it = m->htk_tables.find(static_cast<int>(n_mels));
+  if (it == m->htk_tables.end()) {
+    MelTables t{};
+    int rc = upload_mel_tables(m, htk_filterbank(static_cast<int>(n_mels), N_FFT, 16000), static_cast<int>(n_mels), &t);
+    if (rc != WB_OK) return rc;
+    it = m->htk_tables.emplace(static_cast<int>(n_mels), t).first;
+  }
+  size_t max_frames = 0;
+  for (int i = 0; i < B; ++i) {
+    size_t nf = 0;
+    int rc = mel_compute_one(m, it->second, audio[i], n_samples[i], hop, mels_out[i], out_capacity[i], &nf);
+    if (rc != WB_OK) return rc;
+    frame_counts[i] = nf;
+    max_frames = std::max(max_frames, nf);
+  }
+  if (max_frames_out) *max_frames_out = max_frames;
+  return WB_OK;
 }
 
 static int compute_mel_host(wb_model* m, const float* const* audio, const size_t* n_samples, const float* contiguous, int B,
