@@ -398,3 +398,28 @@ def test_batch_preprocessor_ragged_htk(tiny):
     # a 128-mel preprocessor on the same model handle (tables are per n_mels)
     res128 = BatchPreprocessor(model, n_mels=128).process_batch(batch)
     assert np.abs(res128.mels[1] - M.mel_compute(batch.segments[1], M.htk_filterbank(128))).max() <= MEL_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S", [1500, 700])
+def test_attention_growing_scores_rescale_path(S):
+    """Scores that grow along the keys force the running maximum up block after block, so the lazy rescale of O in tensor memory
+    (only when the max grows by > 2^8) and the alpha-scaled row sum are exercised many times per row; a second head has its
+    largest scores FIRST (no rescale after block 0, tiny later probabilities), a third is flat."""
+    rng = np.random.default_rng(S)
+    H, d = 3, 192
+    qkv = rng.standard_normal((1, S, 3 * d)).astype(np.float32)
+    ramp = np.linspace(0.0, 1.0, S, dtype=np.float32)[:, None]
+    qkv[0, :, 0:64] = 1.0 + 0.1 * qkv[0, :, 0:64]                       # head 0 queries ~ all-ones
+    qkv[0, :, d:d + 64] = (ramp * 9.0) + 0.05 * qkv[0, :, d:d + 64]       # keys: dot product grows to ~ 64 * 9 / 8 = 72 score units
+    qkv[0, :, 64:128] = 1.0 + 0.1 * qkv[0, :, 64:128]
+    qkv[0, :, d + 64:d + 128] = ((1.0 - ramp) * 9.0) + 0.05 * qkv[0, :, d + 64:d + 128]
+    out = np.empty((1, S, d), np.float32)
+    _lib.check(_lib.lib().wb_debug_attention(0, _p(qkv), 1, S, d, H, _p(out)))
+    r = _bf16_round(qkv).astype(np.float64)
+    for h in range(H):
+        q, k, v = (r[0, :, o + h * 64: o + (h + 1) * 64] for o in (0, d, 2 * d))
+        ref = E.naive_attention(q, k, v)
+        got = out[0, :, h * 64:(h + 1) * 64]
+        assert np.isfinite(got).all()
+        assert np.abs(got - ref).max() <= 2.5e-2 and _cos(got, ref) > 0.9999
