@@ -50,7 +50,7 @@ class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_id: str):
         self.rows, self.proc, self.gpu_id = [], None, gpu_id
@@ -79,7 +79,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        loaded = [r for r in self.rows if len(r) > 7 and r[7].replace(".", "", 1).isdigit() and float(r[7]) >= 50.0]
+        for r in (loaded or self.rows):           # samples taken while the GPU was busy; all samples if none qualifies
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):

@@ -6,12 +6,14 @@
 // W stored [out][in]) and Conv1d::forward (src/model/encoder.rs:72-110) of the reference.  Both operands are
 // K-major bf16, accumulation is fp32 in tensor memory.
 //
-// Kernel shape (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: A box {64 k, 128 rows} and W box {64 k, BN rows} per stage, 128-byte swizzle
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / GELU / residual / pos-emb, global stores
-// Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue),
-// static persistent tile schedule with N fastest so CTAs running together share the same A rows through L2.
+// Kernel shape: persistent, a cluster of two CTAs (the two SMs of a TPC, tcgen05 cta_group::2) per 256 x BN tile, 192 threads per CTA:
+//   warp 0      TMA producer: this CTA's 128 rows of A and its half of the W tile per 64-wide k-block, 128-byte swizzle
+//   warp 1      TMEM allocator; in the leader CTA the single-thread issuer of tcgen05.mma.cta_group::2 (256 x BN x 16)
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns (double buffered), per-column scale + bias from shared memory,
+//               GELU; bf16 results and the fp32 residual update leave through shared-memory staging tiles and TMA
+//               (cp.async.bulk.tensor store / cp.reduce.async.bulk.tensor .add) -- no row-per-lane global accesses
+// Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA, multicast commits), two TMEM accumulator buffers (MMA <-> epilogue),
+// static persistent tile schedule with N fastest so CTA pairs running together share the same A rows through L2.
 //
 // The A operand is addressed through a 3-D tensor map [batch][rows][K] with free strides, which is what lets
 // conv1 / conv2 run as GEMMs without materialising im2col: row t of the conv1 operand is the 3*n_mels
@@ -31,16 +33,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = 2 * BN;
-};
 
 struct GemmKParams {
   int rows_per_batch, n_batch, N, K;
@@ -69,68 +61,6 @@ __device__ __forceinline__ float gelu_fast(float x) {
   float u = x + 0.044715f * x * x * x;
   float e = fast_exp2(-c2 * u);
   return __fdividef(x, 1.0f + e);
-}
-
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const GemmKParams& p, const uint32_t (&v)[32], long long out_row, int r_in_batch,
-                                               int n0) {
-  float acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]) * p.alpha;
-  if (p.col_scale != nullptr) {      // per-output-column dequantisation scale (int8 / int4 `.apr` weights)
-    const float4* s4 = reinterpret_cast<const float4*>(p.col_scale + n0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 sc = __ldg(s4 + i);
-      acc[4 * i + 0] *= sc.x; acc[4 * i + 1] *= sc.y; acc[4 * i + 2] *= sc.z; acc[4 * i + 3] *= sc.w;
-    }
-  }
-  if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
-      acc[4 * i + 0] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
-    }
-  }
-  if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_PE_F32) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = gelu_fast(acc[i]);
-  }
-  if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n0;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 w;
-      w.x = pack_bf16x2(acc[8 * i + 0], acc[8 * i + 1]);
-      w.y = pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]);
-      w.z = pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]);
-      w.w = pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]);
-      o4[i] = w;
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n0;
-    float4* o4 = reinterpret_cast<float4*>(o);
-    if constexpr (EPI == EPI_RESID_F32) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 r = o4[i];
-        r.x += acc[4 * i + 0]; r.y += acc[4 * i + 1]; r.z += acc[4 * i + 2]; r.w += acc[4 * i + 3];
-        o4[i] = r;
-      }
-    } else if constexpr (EPI == EPI_GELU_PE_F32) {
-      const float4* pe4 = reinterpret_cast<const float4*>(p.pe + static_cast<long long>(r_in_batch) * p.N + n0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 e = __ldg(pe4 + i);
-        o4[i] = make_float4(acc[4 * i + 0] + e.x, acc[4 * i + 1] + e.y, acc[4 * i + 2] + e.z, acc[4 * i + 3] + e.w);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o4[i] = make_float4(acc[4 * i + 0], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-    }
-  }
 }
 
 // Epilogue of one 32-column chunk for the CTA-pair kernel: acc = v * scale[n] + bias[n] with scale (alpha x per-column
@@ -179,131 +109,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
 #pragma unroll
       for (int i = 0; i < 8; ++i) o4[i] = make_float4(acc[4 * i + 0], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
     }
-  }
-}
-
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
-    fence_mbar_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-
-  const int num_tiles = p.n_batch * p.tiles_m_per_batch * p.tiles_n;
-  const int kblocks = (p.K + BK - 1) / BK;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nb = tile % p.tiles_n;
-        const int mb = tile / p.tiles_n;
-        const int b = mb / p.tiles_m_per_batch;
-        const int mt = mb - b * p.tiles_m_per_batch;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-          tma_load_3d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, mt * BM, b);
-          tma_load_3d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BK, nb * BN, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u;
-        const uint32_t use = it >> 1;
-        mbar_wait(&tempty[buf], (use & 1u) ^ 1u);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty[stage]);       // smem slot free once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(&tfull[buf]);            // accumulator ready for the epilogue
-      }
-    }
-  } else {
-    // -------------------------------------------------------------- epilogue (warps 2..5)
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = it & 1u;
-      const uint32_t use = it >> 1;
-      const int nb = tile % p.tiles_n;
-      const int mb = tile / p.tiles_n;
-      const int b = mb / p.tiles_m_per_batch;
-      const int mt = mb - b * p.tiles_m_per_batch;
-      const int r_in_batch = mt * BM + q * 32 + lane;
-      const bool row_ok = r_in_batch < p.rows_per_batch;
-      const long long out_row = static_cast<long long>(b) * p.out_rows_per_batch + p.out_row_off + r_in_batch;
-      mbar_wait(&tfull[buf], use & 1u);
-      tc_fence_after_sync();
-      const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        const int n0 = nb * BN + c * 32;
-        if (row_ok && n0 < p.N) epilogue_store<EPI>(p, v, out_row, r_in_batch, n0);
-      }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -570,20 +375,6 @@ PFN_tmapEncodeTiled g_encode = nullptr;
 int g_num_sms = 0;
 
 template <int BN, int EPI>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    WB_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM));
-    attr_set = true;
-  }
-  int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  gemm_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, stream>>>(ta, tb, kp);
-  count_launch();
-  WB_CUDA_OK(cudaGetLastError());
-  return WB_OK;
-}
-
-template <int BN, int EPI>
 int launch_variant2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKParams& kp, int num_tiles2, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -606,18 +397,6 @@ int launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     case EPI_RESID_F32: return launch_variant2<BN, EPI_RESID_F32>(ta, tb, tc, kp, num_tiles2, s);
     case EPI_GELU_PE_F32: return launch_variant2<BN, EPI_GELU_PE_F32>(ta, tb, tc, kp, num_tiles2, s);
     case EPI_F32: return launch_variant2<BN, EPI_F32>(ta, tb, tc, kp, num_tiles2, s);
-  }
-  return set_error(WB_ERR_MODEL, "unknown GEMM epilogue");
-}
-
-template <int BN>
-int launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, int num_tiles, cudaStream_t s) {
-  switch (epi) {
-    case EPI_BF16: return launch_variant<BN, EPI_BF16>(ta, tb, kp, num_tiles, s);
-    case EPI_GELU_BF16: return launch_variant<BN, EPI_GELU_BF16>(ta, tb, kp, num_tiles, s);
-    case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32>(ta, tb, kp, num_tiles, s);
-    case EPI_GELU_PE_F32: return launch_variant<BN, EPI_GELU_PE_F32>(ta, tb, kp, num_tiles, s);
-    case EPI_F32: return launch_variant<BN, EPI_F32>(ta, tb, kp, num_tiles, s);
   }
   return set_error(WB_ERR_MODEL, "unknown GEMM epilogue");
 }
@@ -683,9 +462,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   rc = make_tmap_bf16_3d(&ta, g.A, g.K, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.a_row_stride) * 2, batch_stride,
                          BK, BM);
   if (rc != WB_OK) return rc;
-  static const bool one_cta = getenv("WB_GEMM_1CTA") != nullptr;       // bring-up / A-B switch: the CTA-pair kernel is the product path
-  rc = make_tmap_bf16_3d(&tb, g.W, g.K, g.N, 1, static_cast<uint64_t>(g.K) * 2, static_cast<uint64_t>(g.K) * 2 * g.N, BK,
-                         one_cta ? BN : BN / 2);
+  rc = make_tmap_bf16_3d(&tb, g.W, g.K, g.N, 1, static_cast<uint64_t>(g.K) * 2, static_cast<uint64_t>(g.K) * 2 * g.N, BK, BN / 2);
   if (rc != WB_OK) return rc;
   GemmKParams kp;
   kp.rows_per_batch = g.rows_per_batch;
@@ -702,28 +479,23 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.bias = g.bias;
   kp.out = g.out;
   kp.pe = g.pe;
-  if (!one_cta) {
-    const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
-    CUtensorMap tc = ta;                                  // the f32 debug / positional-embedding epilogues do not read it
-    if (g.epilogue == EPI_BF16 || g.epilogue == EPI_GELU_BF16) {
-      __nv_bfloat16* base = static_cast<__nv_bfloat16*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
-      rc = make_tmap_bf16_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 2,
-                             g.n_batch > 1 ? static_cast<uint64_t>(g.out_rows_per_batch) * g.ldc * 2 : static_cast<uint64_t>(g.ldc) * 2 * g.rows_per_batch,
-                             64, 32);
-      if (rc != WB_OK) return rc;
-    }
-    if (g.epilogue == EPI_RESID_F32) {
-      float* base = static_cast<float*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
-      rc = make_tmap_f32_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 4,
-                            static_cast<uint64_t>(g.out_rows_per_batch) * g.ldc * 4, 32, 32);
-      if (rc != WB_OK) return rc;
-    }
-    if (BN == 256) return launch_bn2<256>(g.epilogue, ta, tb, tc, kp, num_tiles2, stream);
-    return launch_bn2<128>(g.epilogue, ta, tb, tc, kp, num_tiles2, stream);
+  const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
+  CUtensorMap tc = ta;                                    // the f32 debug / positional-embedding epilogues do not read it
+  if (g.epilogue == EPI_BF16 || g.epilogue == EPI_GELU_BF16) {
+    __nv_bfloat16* base = static_cast<__nv_bfloat16*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
+    rc = make_tmap_bf16_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 2,
+                           g.n_batch > 1 ? static_cast<uint64_t>(g.out_rows_per_batch) * g.ldc * 2 : static_cast<uint64_t>(g.ldc) * 2 * g.rows_per_batch,
+                           64, 32);
+    if (rc != WB_OK) return rc;
   }
-  const int num_tiles = kp.n_batch * kp.tiles_m_per_batch * kp.tiles_n;
-  if (BN == 256) return launch_bn<256>(g.epilogue, ta, tb, kp, num_tiles, stream);
-  return launch_bn<128>(g.epilogue, ta, tb, kp, num_tiles, stream);
+  if (g.epilogue == EPI_RESID_F32) {
+    float* base = static_cast<float*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
+    rc = make_tmap_f32_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 4,
+                          static_cast<uint64_t>(g.out_rows_per_batch) * g.ldc * 4, 32, 32);
+    if (rc != WB_OK) return rc;
+  }
+  if (BN == 256) return launch_bn2<256>(g.epilogue, ta, tb, tc, kp, num_tiles2, stream);
+  return launch_bn2<128>(g.epilogue, ta, tb, tc, kp, num_tiles2, stream);
 }
 
 }  // namespace wb
