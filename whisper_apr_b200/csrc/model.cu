@@ -288,6 +288,27 @@ int upload_mel_tables(wb_model* m, const std::vector<float>& filt, int n_mels, M
   out->span_lo = d_lo;
   out->span_len = d_len;
   out->n_mels = n_mels;
+  out->packed = nullptr;
+  out->span_off = nullptr;
+  out->nnz = 0;
+  std::vector<int> off(n_mels, 0);
+  std::vector<float> packed;
+  for (int j = 0; j < n_mels; ++j) {                      // every span padded with zero weights to a multiple of 4 (16 B loads)
+    off[j] = static_cast<int>(packed.size());
+    for (int k = 0; k < len[j]; ++k) packed.push_back(filt[static_cast<size_t>(j) * N_FREQ + lo[j] + k]);
+    while (packed.size() % 4 != 0) packed.push_back(0.0f);
+  }
+  if (n_mels <= 256 && packed.size() <= 2048 && !packed.empty()) {
+    float* d_packed;
+    int* d_off;
+    if ((rc = dev_alloc(m, packed.size(), &d_packed)) != WB_OK) return rc;
+    if ((rc = dev_alloc(m, off.size(), &d_off)) != WB_OK) return rc;
+    WB_CUDA_OK(cudaMemcpy(d_packed, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    WB_CUDA_OK(cudaMemcpy(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    out->packed = d_packed;
+    out->span_off = d_off;
+    out->nnz = static_cast<int>(packed.size());
+  }
   return WB_OK;
 }
 

@@ -73,6 +73,11 @@ struct MelTables {                 // device-resident, built at model load
   const int* span_lo;              // [n_mels] first non-zero bin
   const int* span_len;             // [n_mels] bins from first to last non-zero (0 if all-zero row)
   int n_mels;
+  // the same spans packed back to back (row j at packed[span_off[j] .. + span_len[j])): small enough for shared memory when the
+  // bank is triangular (391 weights for slaney-80, ~500 for slaney-128); nullptr when it is not (nnz > 2048 or n_mels > 256)
+  const float* packed;
+  const int* span_off;
+  int nnz;
 };
 // logmel[b][f][j] = log10(max(E,1e-10)) for f < n_frames; chunk_max_key[b] = ordered-int max.
 int launch_mel_stft(const float* audio, long long audio_stride, const int* n_valid, int padded_len, int hop, int n_frames,
