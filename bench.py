@@ -286,6 +286,15 @@ def main():
         e2e = {"value": world * B * CHUNK_SECONDS * args.steps / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": B * synth.N_SAMPLES_30S * 4, "d2h_bytes_per_step": B * S * d * esz, "ms_per_step": ms_e / args.steps}
 
+    # optional final NVLink gather of the step's encoder states: reported beside the step, never inside `value`
+    gather = None
+    if world > 1:
+        from whisper_apr_b200 import sharding
+        for _ in range(2):
+            sharding.gather_states(dev_out, B * world)
+        ms_g = timed(lambda i: sharding.gather_states(dev_out, B * world), 5)
+        gather = {"ms_per_step": ms_g / 5, "bytes_per_rank": dev_out.numel() * dev_out.element_size(), "collective": "nccl all_gather_into_tensor"}
+
     # per-kernel timing (CUDA events on the launching stream) over two more steps of the same region
     peaks = load_peaks()
     model.profile_enable(True)
@@ -343,7 +352,7 @@ def main():
                           "parallelism": f"dp{world} (chunks sharded by batch, replicated weights, no data-path collective)",
                           "setup_s": round(setup_s, 1)},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
-               "cpu_baseline": cpu}
+               "cpu_baseline": cpu, "gather": gather}
         print(json.dumps(out), flush=True)
     model.close()
     if world > 1:

@@ -32,6 +32,11 @@ def gather_states(local, n_chunks: int, group=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    if n_chunks % world == 0 and local.shape[0] == n_chunks // world and local.is_contiguous():
+        # equal shards: one collective straight into the result, no staging copies
+        out = torch.empty((n_chunks,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
     sizes = [shard_range(n_chunks, world, r) for r in range(world)]
     mx = max(e - s for s, e in sizes)
     pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
