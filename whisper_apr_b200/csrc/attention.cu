@@ -65,6 +65,8 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 // packed FFMA2/FADD2 in batches of 16 (0.625), scale+exponentials only under the token with the pack/sum after it (0.627),
 // a second warpgroup per tile on half the columns (0.69), 1-3 of every 8 exponentials as a polynomial on the FMA pipe (+2..+19 %),
 // a run-time loop over 32-column chunks re-read from TMEM with the pack/sum one iteration behind the exponentials (0.60).
+// a streaming block (exponentials against the previous blocks' reference max, chunk by chunk under the tcgen05.ld of the next chunk,
+// no token, deferred O rescale) was correct and 5 % slower (0.553).
 // ptxas also hoists register-only work above the token's bar.sync; pinning the phase behind a post-barrier shared-memory load
 // made it slower (0.549), and made the two-warpgroups-per-tile variant 0.62 instead of 0.73 -- still behind this form.
 // ncu: a lone warp per scheduler issues back-to-back MUFU.EX2 every ~9.5 cycles (8 with two warps), and ptxas places each
