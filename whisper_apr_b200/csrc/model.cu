@@ -8,6 +8,7 @@
 //   transcribe_batch_optimized steps 1-2                   src/lib.rs:1162-1170
 //   split_into_chunks / to_padded_tensor                   src/audio/batch.rs:219-240, 107-127
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -111,6 +112,14 @@ struct wb_model {
   } slot[2];
   int next_slot = 0;
   cudaStream_t in_stream = nullptr, out_stream = nullptr;
+  // CUDA graphs of the fused mel + encoder step, keyed by its device pointers and batch size: the step is 234 launches and as
+  // many host-side tensor-map encodes; a replay is one cudaGraphLaunch.  First sighting of a key runs eagerly, the second is captured.
+  struct StepGraph {
+    const void* in = nullptr; const void* n_valid = nullptr; void* out = nullptr; int B = 0; int dtype = 0;
+    int seen = 0; cudaGraphExec_t exec = nullptr; long long launches = 0;
+  };
+  std::vector<StepGraph> graphs;
+  bool use_graphs = true;
   // per-kernel timing (wb_profile_*): CUDA events recorded on the launching stream around every launch
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;      // start/stop pairs
@@ -462,6 +471,9 @@ int ensure_workspace(wb_model* m, int B) {
   if ((rc = w.out_f32.ensure(b * S * d)) != WB_OK) return rc;
   if ((rc = w.out_bf16.ensure(b * S * d)) != WB_OK) return rc;
   w.cap = B;
+  for (auto& g : m->graphs)                 // workspace pointers are baked into captured launches
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
   return WB_OK;
 }
 
@@ -609,6 +621,7 @@ int wb_model_from_apr(const uint8_t* bytes, size_t n_bytes, int device, wb_model
   wb_model* m = new wb_model();
   m->device = device;
   m->cfg = f.cfg;
+  m->use_graphs = getenv("WB_NO_GRAPH") == nullptr;       // A/B switch: plain launches instead of graph replay
   auto fail = [&](int r) {
     std::string keep = wb::last_error();
     wb_model_free(m);
@@ -642,6 +655,8 @@ void wb_model_free(wb_model* m) {
   w.audio.release(); w.logmel.release(); w.mel_f32.release(); w.x.release(); w.out_f32.release();
   w.n_valid.release(); w.max_key.release();
   w.mel_bf16.release(); w.c1.release(); w.xn.release(); w.qkv.release(); w.att.release(); w.hid.release(); w.out_bf16.release();
+  for (auto& g : m->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& sl : m->slot) {
     sl.audio.release(); sl.n_valid.release(); sl.out.release();
     if (sl.h_n_valid) cudaFreeHost(sl.h_n_valid);
@@ -927,6 +942,60 @@ int wb_encode_batch_dev(const wb_model* cm, const float* d_mel, int B, void* d_o
 }
 
 // ------------------------------------------------------------------------------------- fused hot path
+// One fused mel + encoder step on the model's stream, replayed from a CUDA graph once its (pointers, batch) key has been seen twice.
+static int mel_encode_step(wb_model* m, const float* d_audio, const int* d_n_valid, int nb, void* d_out, wb_dtype out_dtype) {
+  auto eager = [&]() -> int {
+    int rc = mel_device(m, d_audio, d_n_valid, nb, nullptr, true);
+    if (rc != WB_OK) return rc;
+    return encode_device(m, nb, N_FRAMES_30S, d_out, out_dtype, -1, true);
+  };
+  if (!m->use_graphs || m->prof_on) return eager();
+  wb_model::StepGraph* g = nullptr;
+  for (auto& e : m->graphs)
+    if (e.in == d_audio && e.n_valid == d_n_valid && e.out == d_out && e.B == nb && e.dtype == static_cast<int>(out_dtype)) g = &e;
+  if (!g) {
+    if (m->graphs.size() >= 16) {                         // callers that never repeat their pointers do not accumulate graphs
+      for (auto& e : m->graphs)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+      m->graphs.clear();
+    }
+    wb_model::StepGraph e;
+    e.in = d_audio; e.n_valid = d_n_valid; e.out = d_out; e.B = nb; e.dtype = static_cast<int>(out_dtype); e.seen = 1;
+    m->graphs.push_back(e);
+    return eager();
+  }
+  if (g->exec) {
+    WB_CUDA_OK(cudaGraphLaunch(g->exec, m->stream));
+    count_launch(static_cast<int>(g->launches));
+    return WB_OK;
+  }
+  // second sighting: capture the launch sequence (thread-local mode: other threads' CUDA calls are unaffected)
+  const long long before = g_launch_count.load();
+  WB_CUDA_OK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = eager();
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+  if (rc != WB_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    m->use_graphs = false;                                // fall back to plain launches for this model
+    if (rc != WB_OK) return rc;
+    return eager();
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    m->use_graphs = false;
+    return eager();
+  }
+  g->exec = exec;
+  g->launches = g_launch_count.load() - before;
+  WB_CUDA_OK(cudaGraphLaunch(exec, m->stream));
+  return WB_OK;
+}
+
 int wb_mel_encode_batch_dev(const wb_model* cm, const float* d_audio, int B, void* d_out, wb_dtype out_dtype) {
   wb_model* m = const_cast<wb_model*>(cm);
   if (!m || !d_audio || !d_out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
@@ -938,8 +1007,8 @@ int wb_mel_encode_batch_dev(const wb_model* cm, const float* d_audio, int B, voi
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = std::min(m->max_batch, B - b0);
     if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
-    if ((rc = mel_device(m, d_audio + static_cast<size_t>(b0) * N_SAMPLES_30S, nullptr, nb, nullptr, true)) != WB_OK) return rc;
-    if ((rc = encode_device(m, nb, N_FRAMES_30S, static_cast<uint8_t*>(d_out) + static_cast<size_t>(b0) * S * d * esz, out_dtype, -1, true)) != WB_OK)
+    if ((rc = mel_encode_step(m, d_audio + static_cast<size_t>(b0) * N_SAMPLES_30S, nullptr, nb,
+                              static_cast<uint8_t*>(d_out) + static_cast<size_t>(b0) * S * d * esz, out_dtype)) != WB_OK)
       return rc;
   }
   return WB_OK;
@@ -992,8 +1061,7 @@ static int mel_encode_batch_enqueue(wb_model* m, const float* const* audio, cons
     WB_CUDA_OK(cudaMemcpyAsync(sl.n_valid.p, sl.h_n_valid, nb * sizeof(int), cudaMemcpyHostToDevice, m->in_stream));
     WB_CUDA_OK(cudaEventRecord(sl.in_done, m->in_stream));
     WB_CUDA_OK(cudaStreamWaitEvent(m->stream, sl.in_done, 0));
-    if ((rc = mel_device(m, sl.audio.p, sl.n_valid.p, nb, nullptr, true)) != WB_OK) return rc;
-    if ((rc = encode_device(m, nb, N_FRAMES_30S, sl.out.p, out_dtype, -1, true)) != WB_OK) return rc;
+    if ((rc = mel_encode_step(m, sl.audio.p, sl.n_valid.p, nb, sl.out.p, out_dtype)) != WB_OK) return rc;
     WB_CUDA_OK(cudaEventRecord(sl.compute_done, m->stream));
     WB_CUDA_OK(cudaStreamWaitEvent(m->out_stream, sl.compute_done, 0));
     WB_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(out) + static_cast<size_t>(b0) * S * d * esz, sl.out.p, out_bytes, cudaMemcpyDeviceToHost, m->out_stream));
