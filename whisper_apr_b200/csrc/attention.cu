@@ -69,6 +69,12 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 // no token, deferred O rescale) was correct and 5 % slower (0.553).
 // ptxas also hoists register-only work above the token's bar.sync; pinning the phase behind a post-barrier shared-memory load
 // made it slower (0.549), and made the two-warpgroups-per-tile variant 0.62 instead of 0.73 -- still behind this form.
+// Where the time is (measured): with every tcgen05.mma skipped the kernel takes 0.460 ms, i.e. the softmax + synchronisation
+// structure alone runs at ~2530 cycles per 256 x 128 scores = two alternating phases at the lone-warp MUFU rate (microbenchmarks
+// tools/micro/mufu.cu, tmem.cu: 14.5 ex2/clk/SM with one warp per scheduler, 15.9 with two; tcgen05.ld 213 B/clk/SM; neither a
+// concurrent tcgen05.ld stream nor mbarrier polling costs the MUFU rate more than 4 %); the MMAs add 11 %.  Getting under ~0.46 ms
+// needs two warps per scheduler inside the phase, and that variant's phase ran at 13.6 cycles per exponential with MIO-throttle
+// stalls (ncu), for a reason not yet found.
 // ncu: a lone warp per scheduler issues back-to-back MUFU.EX2 every ~9.5 cycles (8 with two warps), and ptxas places each
 // FADD two instructions behind the MUFU pair it consumes, so the phase runs at ~11 cycles per exponential (72 % of the pipe).
 __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb) {
