@@ -264,6 +264,11 @@ def main():
             ms = float(t.item())
         return ms
 
+    # setup, not warm-up: the library captures a step into a CUDA graph the second time it sees a (pointers, batch) key, so every
+    # rotating input buffer is shown to it twice before anything is timed (a capture costs ~10 ms of host time once per key)
+    for i in range(2 * ROT):
+        step_dev(i)
+    torch.cuda.synchronize()
     for i in range(args.warmup):
         step_dev(i)
     gpu_id = str(torch.cuda.get_device_properties(local_rank).uuid)
@@ -278,7 +283,10 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        for i in range(2):
+        for i in range(4):              # both staging slots seen twice: their graphs exist before the timed region
+            step_e2e(i)
+        model.sync()
+        for i in range(max(args.warmup, 2)):
             step_e2e(i)
         model.sync()
         ms_e = timed(step_e2e, args.steps, drain=model.sync)
