@@ -59,3 +59,32 @@ def test_oracle_encoder_matches_hf_whisper_encoder(name):
     assert hf.shape == ours.shape == (1500, cfg.n_audio_state)
     assert np.abs(hf - ours).max() < 1e-6
     assert np.abs(whole - ours).max() < 1e-3
+
+
+def test_oracle_decoder_matches_hf_whisper_decoder():
+    """oracle/decoder.py (forward_one with the KV cache, the decoder the greedy-token gate runs) against HF's WhisperDecoder on the
+    same random tensors: logits of the last position of a 6-token prefix, float64."""
+    from transformers import WhisperConfig
+    from transformers.models.whisper.modeling_whisper import WhisperDecoder
+    from oracle import decoder as D
+    ecfg = E.ModelConfig("toy", 0, 80, 1500, 128, 2, 2, n_vocab=51865, n_text_ctx=32, n_text_state=128, n_text_head=2, n_text_layer=2)
+    w = D.random_decoder_tensors(ecfg, seed=5)
+    hf_cfg = WhisperConfig(d_model=128, decoder_layers=2, decoder_attention_heads=2, decoder_ffn_dim=512, encoder_layers=1,
+                           encoder_attention_heads=2, vocab_size=51865, max_target_positions=32, activation_function="gelu_new",
+                           dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, decoder_layerdrop=0.0, pad_token_id=50256)
+    hf_cfg._attn_implementation = "eager"
+    dec = WhisperDecoder(hf_cfg).double().eval()
+    sd = {k[len("decoder."):]: torch.from_numpy(np.asarray(v, np.float64)) for k, v in w.items()}
+    missing, unexpected = dec.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(".k_proj.bias" in m for m in missing), missing
+    rng = np.random.default_rng(2)
+    enc_states = rng.standard_normal((40, 128))
+    toks = [50258, 50259, 50359, 50363, 11, 4242]
+    with torch.no_grad():
+        h = dec(input_ids=torch.tensor([toks]), encoder_hidden_states=torch.from_numpy(enc_states)[None]).last_hidden_state[0, -1]
+        hf_logits = (dec.embed_tokens.weight @ h).numpy()                    # project_to_vocab: tied embedding (decoder.rs:1794-1806)
+    od = D.Decoder(w, ecfg, enc_states, dtype=np.float64)
+    for t in toks:
+        logits = od.forward_one(t)
+    assert np.abs(logits - hf_logits).max() < 1e-6        # 2e-8: the reference rounds sqrt(2/pi) to 0.7978846
