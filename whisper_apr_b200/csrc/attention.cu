@@ -74,7 +74,10 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 // tools/micro/mufu.cu, tmem.cu: 14.5 ex2/clk/SM with one warp per scheduler, 15.9 with two; tcgen05.ld 213 B/clk/SM; neither a
 // concurrent tcgen05.ld stream nor mbarrier polling costs the MUFU rate more than 4 %); the MMAs add 11 %.  Getting under ~0.46 ms
 // needs two warps per scheduler inside the phase, and that variant's phase ran at 13.6 cycles per exponential with MIO-throttle
-// stalls (ncu), for a reason not yet found.
+// stalls (ncu).  The mechanism (SASS): ptxas hoists every FADD / F2FP to the slot right behind the MUFU pair that produces its
+// operands -- also when the source issues the exponentials as `asm volatile` groups and consumes them a group later -- so a warp
+// waits out the MUFU latency (~22 cycles alone, ~35 behind a second warp's queue) once per pair: 11 cycles per exponential with one
+// warp per scheduler, 13 with two.  The microbenchmark keeps 8 exponentials between producer and consumer and reaches the pipe rate.
 // ncu: a lone warp per scheduler issues back-to-back MUFU.EX2 every ~9.5 cycles (8 with two warps), and ptxas places each
 // FADD two instructions behind the MUFU pair it consumes, so the phase runs at ~11 cycles per exponential (72 % of the pipe).
 __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb) {
