@@ -172,6 +172,9 @@ int wb_profile_enable(wb_model* m, int on);
 int wb_profile_read(wb_model* m, float* ms_by_cat, int* launches_by_cat, int n_cat);
 /* Number of CUDA kernels this library has launched in this process (all models). */
 long long wb_launch_count(void);
+/* Payload bytes AprReader::load_tensor would read for `name` (src/format/mod.rs:610-628): >= 0, -1 when the tensor is absent or its
+ * descriptor points outside the file ("tensor data out of bounds"), -2 when the container does not parse.  No GPU needed. */
+long long wb_debug_apr_tensor_bytes(const uint8_t* bytes, size_t n_bytes, const char* name);
 /* LayerNorm rows: x f32 [rows][d] -> out f32 (exact f32 result) */
 int wb_debug_layernorm(int device, const float* x, const float* gamma, const float* beta, int rows, int d, float* out);
 

@@ -94,3 +94,53 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
                 assert "oracle/" not in src or f.endswith(".md"), f"{f} references oracle/"
+
+
+def test_hostile_tensor_descriptor_is_out_of_bounds():
+    """A descriptor whose n_elements / offset would wrap 64-bit arithmetic must read as "tensor data out of bounds"
+    (format/mod.rs:610-628), for every payload type; a sane one reports its byte count."""
+    import struct
+    lib = _lib.lib()
+    cfg = synth.ModelConfig("t", 0, 80, 1500, 128, 2, 1, 51865, 448, 128, 2, 1)
+    for quant, per in ((0, 4.0), (2, 1.0), (3, 0.5)):
+        data = bytearray(synth.random_model_apr(cfg, quant=quant)[0])
+        name = b"encoder.conv1.bias"
+        buf = (C.c_ubyte * len(data)).from_buffer(data)
+        assert lib.wb_debug_apr_tensor_bytes(buf, len(data), name) == int(128 * per)
+        assert lib.wb_debug_apr_tensor_bytes(buf, len(data), b"no.such.tensor") == -1
+        # descriptor 1 is conv1.bias: offset @ +48, n_elements @ +64
+        base = 4 + 48 + 96 * 1
+        assert bytes(data[base:base + len(name)]) == name
+        for n_elem in (1 << 62, (1 << 64) - 1, 1 << 63, len(data) * 8):
+            bad = bytearray(data)
+            struct.pack_into("<Q", bad, base + 64, n_elem)
+            b2 = (C.c_ubyte * len(bad)).from_buffer(bad)
+            assert lib.wb_debug_apr_tensor_bytes(b2, len(bad), name) == -1, (quant, n_elem)
+        for off in ((1 << 64) - 8, (1 << 63), len(data)):
+            bad = bytearray(data)
+            struct.pack_into("<Q", bad, base + 48, off)
+            b2 = (C.c_ubyte * len(bad)).from_buffer(bad)
+            assert lib.wb_debug_apr_tensor_bytes(b2, len(bad), name) == -1, (quant, off)
+    assert lib.wb_debug_apr_tensor_bytes(None, 0, b"x") == -2
+
+
+def test_unreasonable_header_dimensions_are_refused():
+    import struct
+    data = bytearray(synth.random_model_apr(synth.ModelConfig("t", 0, 80, 1500, 128, 2, 1, 51865, 448, 128, 2, 1))[0])
+    struct.pack_into("<I", data, 4 + 16, 1 << 30)          # n_audio_state
+    with pytest.raises(WhisperError) as e:
+        WhisperApr.load_from_apr(bytes(data))
+    assert e.value.kind == "Format" and "unreasonable model dimensions" in str(e.value)
+
+
+def test_caller_supplied_out_buffer_is_validated():
+    from whisper_apr_b200 import api
+    api._check_out(np.empty((2, 1500, 384), np.float32), (2, 1500, 384), np.float32)
+    for bad in (np.empty((2, 1500, 384), np.float64), np.empty((2, 1500, 383), np.float32),
+                np.empty((2, 1500, 768), np.float32)[:, :, ::2], [1, 2, 3]):
+        with pytest.raises((ValueError, TypeError)):
+            api._check_out(bad, (2, 1500, 384), np.float32)
+    ro = np.empty((2, 1500, 384), np.float32)
+    ro.setflags(write=False)
+    with pytest.raises(ValueError):
+        api._check_out(ro, (2, 1500, 384), np.float32)

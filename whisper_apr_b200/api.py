@@ -34,6 +34,16 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _check_out(out, shape, dtype) -> None:
+    """A caller-supplied result buffer is written through its raw pointer by the C ABI: refuse anything that is not exactly
+    the array the library will fill."""
+    if not isinstance(out, np.ndarray):
+        raise TypeError("out must be a numpy array")
+    if out.dtype != np.dtype(dtype) or tuple(out.shape) != tuple(shape) or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+        raise ValueError(f"out must be a writable C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}, "
+                         f"got {out.dtype.name} {tuple(out.shape)}")
+
+
 @dataclass
 class BatchEncoderOutput:
     """model/encoder.rs:673-720."""
@@ -183,12 +193,12 @@ class WhisperApr:
         B = len(chunks)
         d = self.config.n_audio_state
         S = (N_FRAMES_30S - 1) // 2 + 1
-        if out_dtype == "f32":
-            out = np.empty((B, S, d), np.float32) if out is None else out
-            code = WB_F32
+        want = np.float32 if out_dtype == "f32" else np.uint16              # uint16: raw bf16 bits
+        code = WB_F32 if out_dtype == "f32" else WB_BF16
+        if out is None:
+            out = np.empty((B, S, d), want)
         else:
-            out = np.empty((B, S, d), np.uint16) if out is None else out    # raw bf16 bits
-            code = WB_BF16
+            _check_out(out, (B, S, d), want)
         if B == 0:
             return out
         ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in chunks])
@@ -199,6 +209,11 @@ class WhisperApr:
     def mel_encode_batch_async(self, audio_batch, out: np.ndarray, out_dtype: str = "f32"):
         """Enqueue form of mel_encode_batch: `audio_batch` (contiguous f32 arrays) and `out` must stay alive until sync()."""
         B = len(audio_batch)
+        d = self.config.n_audio_state
+        _check_out(out, (B, (N_FRAMES_30S - 1) // 2 + 1, d), np.float32 if out_dtype == "f32" else np.uint16)
+        for a in audio_batch:
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("mel_encode_batch_async needs C-contiguous float32 arrays (they are read after the call returns)")
         ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in audio_batch])
         lens = (C.c_size_t * B)(*[a.size for a in audio_batch])
         check(_lib.lib().wb_mel_encode_batch_async(self._h, ptrs, lens, B, _ptr(out), WB_F32 if out_dtype == "f32" else WB_BF16))

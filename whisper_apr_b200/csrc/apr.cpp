@@ -32,15 +32,27 @@ const AprTensor* AprFile::find(const std::string& name) const {
 }
 
 const uint8_t* AprFile::payload(const AprTensor& t, size_t* n_out) const {
-  size_t need;
-  switch (cfg.quantization) {
-    case 2: need = t.n_elements; break;                 // int8: one byte per element (format/mod.rs:653-655)
-    case 3: need = (t.n_elements + 1) / 2; break;       // int4 (defined extension): two per byte
-    default: need = t.n_elements * 4; break;            // everything else is read as f32 (format/mod.rs:619-628)
-  }
+  // every bound is checked by subtraction / division so that a hostile descriptor (n_elements >= 2^62, offset near 2^64) cannot
+  // wrap: the reference answers "tensor data out of bounds" for all of them (format/mod.rs:610-628)
+  if (data_offset > n_bytes || t.offset > n_bytes - data_offset) return nullptr;
   const uint64_t start = static_cast<uint64_t>(data_offset) + t.offset;
-  if (start > n_bytes || need > n_bytes - start) return nullptr;
-  *n_out = need;
+  const uint64_t avail = n_bytes - start;
+  uint64_t need;
+  switch (cfg.quantization) {
+    case 2:                                             // int8: one byte per element (format/mod.rs:653-655)
+      if (t.n_elements > avail) return nullptr;
+      need = t.n_elements;
+      break;
+    case 3:                                             // int4 (defined extension): two per byte
+      if (t.n_elements / 2 > avail || (t.n_elements + 1) / 2 > avail) return nullptr;
+      need = (t.n_elements + 1) / 2;
+      break;
+    default:                                            // everything else is read as f32 (format/mod.rs:619-628)
+      if (t.n_elements > avail / 4) return nullptr;
+      need = t.n_elements * 4;
+      break;
+  }
+  *n_out = static_cast<size_t>(need);
   return bytes + start;
 }
 

@@ -323,19 +323,15 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
   }
 }
 
-bool g_tm_init = false;
-int g_tm_sms = 0;
+PerDeviceOnce g_tm_once;
 
 }  // namespace
 
 int attention_init() {
-  if (g_tm_init) return WB_OK;
-  WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
-  int dev = 0;
-  WB_CUDA_OK(cudaGetDevice(&dev));
-  WB_CUDA_OK(cudaDeviceGetAttribute(&g_tm_sms, cudaDevAttrMultiProcessorCount, dev));
-  g_tm_init = true;
-  return WB_OK;
+  return g_tm_once.run([](int) -> int {
+    WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+    return WB_OK;
+  });
 }
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream) {
@@ -357,7 +353,8 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S,
   p.out = out;
   static const int no_token = getenv("WB_ATTN_NOTOKEN") != nullptr;       // tuning switch
   p.use_token = no_token ? 0 : 1;
-  const int grid = p.n_items < g_tm_sms ? p.n_items : g_tm_sms;
+  const int sms = device_sm_count();
+  const int grid = p.n_items < sms ? p.n_items : sms;
   attention_tm_kernel<<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());

@@ -371,17 +371,17 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_tmapEncodeTiled g_encode = nullptr;
-int g_num_sms = 0;
+std::atomic<PFN_tmapEncodeTiled> g_encode{nullptr};
 
 template <int BN, int EPI>
 int launch_variant2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKParams& kp, int num_tiles2, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;                               // the shared-memory opt-in is a per-device (per-context) attribute
+  int rc = once.run([](int) -> int {
     WB_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM));
-    attr_set = true;
-  }
-  int pairs = g_num_sms / 2;
+    return WB_OK;
+  });
+  if (rc != WB_OK) return rc;
+  int pairs = device_sm_count() / 2;
   if (num_tiles2 < pairs) pairs = num_tiles2;
   gemm2_tn_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM, stream>>>(ta, tb, tc, kp);
   count_launch();
@@ -403,17 +403,24 @@ int launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUte
 
 }  // namespace
 
+int device_sm_count() {
+  static std::atomic<int> sms[WB_MAX_DEVICES];
+  const int dev = current_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  sms[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
 int gemm_init() {
-  if (g_encode != nullptr) return WB_OK;
+  if (g_encode.load(std::memory_order_acquire) != nullptr) return WB_OK;      // a driver entry point: process-wide, not per device
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   WB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
     return set_error(WB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
-  int dev = 0;
-  WB_CUDA_OK(cudaGetDevice(&dev));
-  WB_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  g_encode.store(reinterpret_cast<PFN_tmapEncodeTiled>(fn), std::memory_order_release);
   return WB_OK;
 }
 
@@ -425,7 +432,7 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode.load(std::memory_order_acquire)(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -445,7 +452,7 @@ static int make_tmap_f32_3d(CUtensorMap* out, void* base, uint64_t d0, uint64_t 
   cuuint64_t strides[2] = {stride1_bytes, d2 > 1 ? stride2_bytes : stride1_bytes * d1};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = g_encode.load(std::memory_order_acquire)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(WB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the f32 output view (" + std::to_string(static_cast<int>(r)) + ")");
   return WB_OK;

@@ -185,6 +185,7 @@ mel_stft_kernel(const float* __restrict__ audio, long long audio_stride, const i
       }
     }
   }
+  if (tid < 4) s.p[FT * PSTRIDE + tid] = 0.f;      // the zero-weighted padding of the last span reads up to 3 floats past bin 200 of the last frame
   __syncthreads();
 
   // ---- filterbank over non-zero spans, log10, store, running max
@@ -291,37 +292,40 @@ mel_finalize_scalar_kernel(const float* __restrict__ logmel, const int* __restri
   if (out_bf16) out_bf16[static_cast<long long>(b) * (T_out + 2) * m + m + i] = __float2bfloat16_rn(v);
 }
 
-float2* g_tw200 = nullptr;
-float2* g_tw400 = nullptr;
+// twiddle tables live on ONE device; a process that drives several GPUs gets a set per device (PerDeviceOnce)
+float2* g_tw200[WB_MAX_DEVICES] = {};
+float2* g_tw400[WB_MAX_DEVICES] = {};
+PerDeviceOnce g_mel_once;
 
 }  // namespace
 
 int mel_init() {
-  if (g_tw200 != nullptr) return WB_OK;
-  const double PI = 3.14159265358979323846;
-  float2 tw25[25], tw200[200], tw400[NFREQ + 1];
-  for (int bb = 0; bb < 5; ++bb)
-    for (int c = 0; c < 5; ++c) {
-      double a = -2.0 * PI * bb * c / 25.0;
-      tw25[bb * 5 + c] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+  return g_mel_once.run([](int dev) -> int {
+    const double PI = 3.14159265358979323846;
+    float2 tw25[25], tw200[200], tw400[NFREQ + 1];
+    for (int bb = 0; bb < 5; ++bb)
+      for (int c = 0; c < 5; ++c) {
+        double a = -2.0 * PI * bb * c / 25.0;
+        tw25[bb * 5 + c] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+      }
+    for (int n2 = 0; n2 < 8; ++n2)
+      for (int k1 = 0; k1 < 25; ++k1) {
+        double a = -2.0 * PI * n2 * k1 / 200.0;
+        tw200[n2 * 25 + k1] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+      }
+    for (int k = 0; k <= NFREQ; ++k) {
+      double a = -2.0 * PI * k / 400.0;
+      tw400[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
     }
-  for (int n2 = 0; n2 < 8; ++n2)
-    for (int k1 = 0; k1 < 25; ++k1) {
-      double a = -2.0 * PI * n2 * k1 / 200.0;
-      tw200[n2 * 25 + k1] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
-    }
-  for (int k = 0; k <= NFREQ; ++k) {
-    double a = -2.0 * PI * k / 400.0;
-    tw400[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
-  }
-  WB_CUDA_OK(cudaMemcpyToSymbol(c_tw25, tw25, sizeof tw25));
-  WB_CUDA_OK(cudaMalloc(&g_tw200, sizeof tw200));
-  WB_CUDA_OK(cudaMalloc(&g_tw400, sizeof tw400));
-  WB_CUDA_OK(cudaMemcpy(g_tw200, tw200, sizeof tw200, cudaMemcpyHostToDevice));
-  WB_CUDA_OK(cudaMemcpy(g_tw400, tw400, sizeof tw400, cudaMemcpyHostToDevice));
-  WB_CUDA_OK(cudaFuncSetAttribute(mel_stft_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
-  WB_CUDA_OK(cudaFuncSetAttribute(mel_stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
-  return WB_OK;
+    WB_CUDA_OK(cudaMemcpyToSymbol(c_tw25, tw25, sizeof tw25));
+    WB_CUDA_OK(cudaMalloc(&g_tw200[dev], sizeof tw200));
+    WB_CUDA_OK(cudaMalloc(&g_tw400[dev], sizeof tw400));
+    WB_CUDA_OK(cudaMemcpy(g_tw200[dev], tw200, sizeof tw200, cudaMemcpyHostToDevice));
+    WB_CUDA_OK(cudaMemcpy(g_tw400[dev], tw400, sizeof tw400, cudaMemcpyHostToDevice));
+    WB_CUDA_OK(cudaFuncSetAttribute(mel_stft_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
+    WB_CUDA_OK(cudaFuncSetAttribute(mel_stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
+    return WB_OK;
+  });
 }
 
 int launch_mel_stft(const float* audio, long long audio_stride, const int* n_valid, int padded_len, int hop, int n_frames, int B,
@@ -329,6 +333,7 @@ int launch_mel_stft(const float* audio, long long audio_stride, const int* n_val
   int rc = mel_init();
   if (rc != WB_OK) return rc;
   if (B <= 0 || n_frames <= 0) return WB_OK;
+  const int dev = current_device();
   mel_init_max_kernel<<<(B + 255) / 256, 256, 0, stream>>>(chunk_max_key, B);
   count_launch();
   int fpt = FT;
@@ -341,10 +346,10 @@ int launch_mel_stft(const float* audio, long long audio_stride, const int* n_val
   const bool fast = hop == 160 && (audio_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(audio) & 15) == 0);
   if (fast) {
     mel_stft_kernel<160><<<grid, MEL_THREADS, sizeof(MelSmem), stream>>>(audio, audio_stride, n_valid, padded_len, hop, n_frames,
-                                                                         fpt, t, g_tw200, g_tw400, logmel, chunk_max_key);
+                                                                         fpt, t, g_tw200[dev], g_tw400[dev], logmel, chunk_max_key);
   } else {
     mel_stft_kernel<0><<<grid, MEL_THREADS, sizeof(MelSmem), stream>>>(audio, audio_stride, n_valid, padded_len, hop, n_frames, fpt,
-                                                                       t, g_tw200, g_tw400, logmel, chunk_max_key);
+                                                                       t, g_tw200[dev], g_tw400[dev], logmel, chunk_max_key);
   }
   count_launch();
   WB_CUDA_OK(cudaGetLastError());

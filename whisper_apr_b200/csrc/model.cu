@@ -43,6 +43,10 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }                 // every early return (WB_CUDA_OK) gives the memory back
   int ensure(size_t count) {
     if (count <= n) return WB_OK;
     if (p) cudaFree(p);
@@ -56,6 +60,20 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
+  }
+};
+
+struct EventPair {                         // timing events that cannot leak on an early return
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  EventPair() {
+    if (cudaEventCreate(&e0) != cudaSuccess) e0 = nullptr;
+    if (cudaEventCreate(&e1) != cudaSuccess) e1 = nullptr;
+  }
+  EventPair(const EventPair&) = delete;
+  EventPair& operator=(const EventPair&) = delete;
+  ~EventPair() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
   }
 };
 
@@ -338,7 +356,9 @@ int build_mel_tables(wb_model* m, const AprFile& f) {
 
 int load_weights(wb_model* m, const AprFile& f) {
   const size_t d = m->cfg.n_audio_state, nm = m->cfg.n_mels, L = m->cfg.n_audio_layer, ctx = m->cfg.n_audio_ctx;
-  Uploader up{m, &f, {}};
+  Uploader up;
+  up.m = m;
+  up.f = &f;
   int rc = WB_OK;
   const bool quant = f.cfg.quantization == 2 || f.cfg.quantization == 3;
   auto done = [&](int r) { up.staging.release(); return r; };
@@ -453,8 +473,11 @@ int load_weights(wb_model* m, const AprFile& f) {
 int ensure_workspace(wb_model* m, int B) {
   Workspace& w = m->ws;
   if (B <= w.cap) return WB_OK;
-  const size_t d = m->cfg.n_audio_state, nm = std::max<size_t>(m->cfg.n_mels, m->mel.n_mels), S = m->cfg.n_audio_ctx;
-  const size_t T = N_FRAMES_30S, b = static_cast<size_t>(B);
+  // a mel of T frames gives S = (T - 1) / 2 + 1 <= n_audio_ctx positions (validate_mel_len), so T <= 2 * ctx; the fused paths
+  // always run T = 3000 / S = 1500 and are refused up front when the header's n_audio_ctx is smaller (check_fused_dims)
+  const size_t d = m->cfg.n_audio_state, nm = std::max<size_t>(m->cfg.n_mels, m->mel.n_mels);
+  const size_t S = std::max<size_t>(m->cfg.n_audio_ctx, (N_FRAMES_30S - 1) / 2 + 1);
+  const size_t T = std::max<size_t>(N_FRAMES_30S, 2 * static_cast<size_t>(m->cfg.n_audio_ctx)), b = static_cast<size_t>(B);
   int rc;
   if ((rc = w.audio.ensure(b * N_SAMPLES_30S)) != WB_OK) return rc;
   if ((rc = w.n_valid.ensure(b)) != WB_OK) return rc;
@@ -581,6 +604,17 @@ int check_encoder_dims(const wb_model* m) {
   return WB_OK;
 }
 
+// The fused 30 s paths always produce 1500 positions: a header with a smaller n_audio_ctx gets the reference's own error
+// (Encoder::forward, encoder.rs:456-461) instead of a workspace / positional-embedding overrun.
+int check_fused_dims(const wb_model* m) {
+  int rc = check_encoder_dims(m);
+  if (rc != WB_OK) return rc;
+  const size_t S = (N_FRAMES_30S - 1) / 2 + 1;
+  if (S > m->cfg.n_audio_ctx)
+    return set_error(WB_ERR_MODEL, "sequence length " + std::to_string(S) + " exceeds max " + std::to_string(m->cfg.n_audio_ctx));
+  return WB_OK;
+}
+
 }  // namespace
 }  // namespace wb
 
@@ -608,15 +642,19 @@ int wb_model_from_apr(const uint8_t* bytes, size_t n_bytes, int device, wb_model
   int rc = parse_apr(bytes, n_bytes, &f);
   if (rc != WB_OK) return rc;
   if (f.cfg.quantization == 1) return set_error(WB_ERR_FORMAT, "F16 .apr payloads have no reader (as in the reference)");
+  // an untrusted header sizes every device allocation: refuse dimensions no Whisper variant comes near
+  if (f.cfg.n_audio_state > 16384 || f.cfg.n_audio_layer > 512 || f.cfg.n_audio_ctx > 65536 || f.cfg.n_mels > 1024 ||
+      f.cfg.n_audio_head > 256)
+    return set_error(WB_ERR_FORMAT, "unreasonable model dimensions in the .apr header");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
     return set_error(WB_ERR_CUDA, "no CUDA device: libwhisper_b200 has no CPU fallback");
   }
   if (device < 0 || device >= ndev) return set_error(WB_ERR_CUDA, "invalid CUDA device ordinal");
-  cudaDeviceProp prop;
-  WB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) return set_error(WB_ERR_CUDA, std::string("kernels are built for sm_100a only; device is ") + prop.name);
+  int cc_major = 0;
+  WB_CUDA_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  if (cc_major != 10) return set_error(WB_ERR_CUDA, "kernels are built for sm_100a only; device has compute capability " + std::to_string(cc_major) + ".x");
   DeviceGuard guard(device);
   wb_model* m = new wb_model();
   m->device = device;
@@ -635,7 +673,8 @@ int wb_model_from_apr(const uint8_t* bytes, size_t n_bytes, int device, wb_model
   if ((rc = build_mel_tables(m, f)) != WB_OK) return fail(rc);
   if (m->cfg.n_mels == 0) m->cfg.n_mels = m->mel.n_mels;
   if ((rc = load_weights(m, f)) != WB_OK) return fail(rc);
-  WB_CUDA_OK(cudaStreamSynchronize(m->stream));
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess)
+    return fail(set_error(WB_ERR_CUDA, std::string("model upload failed: ") + cudaGetErrorString(cudaGetLastError())));
   *out = m;
   return WB_OK;
 }
@@ -933,7 +972,7 @@ int wb_encode_batch(const wb_model* cm, const float* const* mels, const size_t* 
 int wb_encode_batch_dev(const wb_model* cm, const float* d_mel, int B, void* d_out, wb_dtype out_dtype) {
   wb_model* m = const_cast<wb_model*>(cm);
   if (!m || !d_mel || !d_out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
-  int rc = check_encoder_dims(m);
+  int rc = check_fused_dims(m);
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
@@ -999,7 +1038,7 @@ static int mel_encode_step(wb_model* m, const float* d_audio, const int* d_n_val
 int wb_mel_encode_batch_dev(const wb_model* cm, const float* d_audio, int B, void* d_out, wb_dtype out_dtype) {
   wb_model* m = const_cast<wb_model*>(cm);
   if (!m || !d_audio || !d_out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
-  int rc = check_encoder_dims(m);
+  int rc = check_fused_dims(m);
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
@@ -1074,7 +1113,7 @@ static int mel_encode_batch_enqueue(wb_model* m, const float* const* audio, cons
 int wb_mel_encode_batch_async(const wb_model* cm, const float* const* audio, const size_t* n_samples, int B, void* out, wb_dtype out_dtype) {
   wb_model* m = const_cast<wb_model*>(cm);
   if (!m || !audio || !n_samples || !out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
-  int rc = check_encoder_dims(m);
+  int rc = check_fused_dims(m);
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
@@ -1220,9 +1259,9 @@ int wb_debug_gemm_bench(int device, int n_batch, int rows, int N, int K, int epi
   g.ldc = N; g.out_rows_per_batch = rows; g.out_row_off = 0; g.pe = nullptr;
   g.out = bf_out ? static_cast<void*>(bo.p) : static_cast<void*>(fo.p);
   if (epilogue == EPI_GELU_PE_F32) return cleanup(set_error(WB_ERR_MODEL, "pe epilogue not benchmarked"));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
+  if (!e0 || !e1) return cleanup(set_error(WB_ERR_CUDA, "cudaEventCreate failed"));
   for (int i = 0; i < 2; ++i)
     if ((rc = launch_gemm(g, nullptr)) != WB_OK) return cleanup(rc);
   cudaEventRecord(e0, nullptr);
@@ -1233,8 +1272,6 @@ int wb_debug_gemm_bench(int device, int n_batch, int rows, int N, int K, int epi
   if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("gemm kernel failed: ") + cudaGetErrorString(e)));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   *ms_per_launch = ms / iters;
   return cleanup(WB_OK);
 }
@@ -1257,9 +1294,9 @@ int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int i
   cudaMemcpy(f.p, h.data(), per * 4, cudaMemcpyHostToDevice);
   launch_f32_to_bf16(f.p, bq.p, per, nullptr);
   for (int b = 1; b < B; ++b) cudaMemcpyAsync(bq.p + b * per, bq.p, per * 2, cudaMemcpyDeviceToDevice, nullptr);
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
+  if (!e0 || !e1) return cleanup(set_error(WB_ERR_CUDA, "cudaEventCreate failed"));
   for (int i = 0; i < 2; ++i)
     if ((rc = launch_attention(bq.p, bo.p, B, S, d, n_heads, nullptr)) != WB_OK) return cleanup(rc);
   cudaEventRecord(e0, nullptr);
@@ -1270,13 +1307,20 @@ int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int i
   if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("attention kernel failed: ") + cudaGetErrorString(e)));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   *ms_per_launch = ms / iters;
   return cleanup(WB_OK);
 }
 
 long long wb_launch_count(void) { return wb::g_launch_count.load(); }
+
+long long wb_debug_apr_tensor_bytes(const uint8_t* bytes, size_t n_bytes, const char* name) {
+  AprFile f;
+  if (!name || parse_apr(bytes, n_bytes, &f) != WB_OK) return -2;
+  const AprTensor* t = f.find(name);
+  if (!t) return -1;
+  size_t nb = 0;
+  return f.payload(*t, &nb) ? static_cast<long long>(nb) : -1;      // -1: "tensor data out of bounds" (format/mod.rs:610-628)
+}
 
 int wb_profile_enable(wb_model* m, int on) {
   if (!m) return set_error(WB_ERR_MODEL, "null model");

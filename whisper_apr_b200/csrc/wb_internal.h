@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/whisper_b200.h"
@@ -22,6 +23,34 @@ const char* last_error();
     if (_e != cudaSuccess)                                                                       \
       return ::wb::set_error(WB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
   } while (0)
+
+// ---- per-device one-time initialisation.  Kernel attributes (opt-in shared memory), __constant__ tables and small device
+// tables belong to ONE device's context: a process that drives several GPUs (wb_model_from_apr_devices, or two models on two
+// ordinals) must set them up on each.  `run(fn)` calls fn() once per CUDA device, on the calling thread's current device.
+constexpr int WB_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= WB_MAX_DEVICES) return 0;
+  return dev;
+}
+struct PerDeviceOnce {
+  std::mutex mu;
+  std::atomic<bool> done[WB_MAX_DEVICES];
+  PerDeviceOnce() {
+    for (auto& d : done) d.store(false);
+  }
+  template <typename F>
+  int run(F&& fn) {
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire)) return WB_OK;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev].load(std::memory_order_relaxed)) return WB_OK;
+    const int rc = fn(dev);
+    if (rc == WB_OK) done[dev].store(true, std::memory_order_release);
+    return rc;
+  }
+};
+int device_sm_count();   // SM count of the current device (cached per device)
 
 // every kernel launch of the library bumps this (bench.py reports it as gpu_launches)
 extern std::atomic<long long> g_launch_count;
