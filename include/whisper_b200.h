@@ -59,6 +59,9 @@ typedef struct wb_config {
 /* Output element type of the fused batch entry point. */
 typedef enum wb_dtype { WB_F32 = 0, WB_BF16 = 1 } wb_dtype;
 
+/* On-device requantisation modes of wb_model_requantize. */
+#define WB_QUANT_INT8_PER_CHANNEL 1
+
 /* ---- library ---------------------------------------------------------------------- */
 const char* wb_version(void);
 /* WhisperError Display (src/error.rs).  Thread-local; valid until the next failing call. */
@@ -75,6 +78,21 @@ int wb_device_count(void);
  * exactly as the reference loader does.  Int8 / Int4 weights stay packed on the host side of
  * the upload and are expanded on the device.  `device` is the CUDA ordinal. */
 int wb_model_from_apr(const uint8_t* bytes, size_t n_bytes, int device, wb_model** out);
+/* The same load onto a SET of devices of this process: weights and filterbank are replicated (one host thread per device pulls the
+ * caller's page-locked bytes over that device's own link), every device gets its own streams and workspace.  This is what
+ * parallel::configure_thread_pool (src/parallel.rs:34-60) becomes on a box of B200s: the handle's device list is the pool.
+ * wb_mel_encode_batch{,_async}, wb_mel_encode_gather and wb_transcribe_tokens_batch shard their chunks over the list
+ * (chunk i of B -> device floor(i * n_devices / B): contiguous blocks, order preserved like parallel_map, src/parallel.rs:82-118);
+ * every other entry point runs on devices[0]. */
+int wb_model_from_apr_devices(const uint8_t* bytes, size_t n_bytes, const int* devices, int n_devices, wb_model** out);
+/* parallel::thread_count for a handle: the number of devices it spans; and the CUDA ordinal of its index-th device (-1 if out of range). */
+int wb_model_n_devices(const wb_model* m);
+int wb_model_device(const wb_model* m, int index);
+/* Requantise the resident bf16 linear weights on the device.  WB_QUANT_INT8_PER_CHANNEL: quantize_f32_to_i8_per_channel
+ * (src/model/quantized.rs:1769-1794) -- one scale = absmax / 127 per output channel, round half away from zero, clamp [-128, 127];
+ * the int8 rows replace the bf16 matrices in HBM (1 B per weight) and the per-channel scale is applied per output column in the GEMM
+ * epilogue, which is dequantize_i8_to_f32_per_channel (:1797-1813) folded into the product.  Needs a model loaded from f32 payloads. */
+int wb_model_requantize(wb_model* m, int mode);
 /* WhisperApr::config (src/lib.rs:330-333). */
 int wb_model_config(const wb_model* m, wb_config* out);
 void wb_model_free(wb_model* m);
@@ -129,8 +147,44 @@ int wb_mel_encode_batch_dev(const wb_model* m, const float* d_audio, int B, void
 /* Device-resident pieces of the same path, for per-kernel measurement. */
 int wb_compute_mel_batch_dev(const wb_model* m, const float* d_audio, int B, float* d_mel_out);
 int wb_encode_batch_dev(const wb_model* m, const float* d_mel, int B, void* d_out, wb_dtype out_dtype);
-/* Block until the model's stream is idle. */
+/* Block until every device of the handle is idle. */
 int wb_sync(const wb_model* m);
+/* The sharded call with the encoder states left ON A DEVICE ("a final NVLink gather of encoder states"): the device at
+ * index `gather_index` of the handle's list receives all B chunks' states, [B][1500][d] in chunk order, in a library-owned buffer
+ * returned in *d_states_out (valid until the next gather call on the handle; complete after wb_sync, and ordered before any work
+ * enqueued afterwards on that device's stream).  The other devices' final LayerNorm kernels store their rows straight into that
+ * buffer over NVLink -- peer stores issued by the compute kernel itself, micro-batch by micro-batch, so the transfer overlaps the
+ * next micro-batch: no staging copy, no extra pass, no NCCL call. */
+int wb_mel_encode_gather(const wb_model* m, const float* const* audio, const size_t* n_samples, int B, wb_dtype out_dtype,
+                         int gather_index, void** d_states_out);
+/* Peer-visible device buffers across PROCESSES (one process per GPU under torchrun): the gather rank allocates and exports its states
+ * buffer (64-byte cudaIpcMemHandle), the other ranks open it and pass `peer + offset` as d_out of wb_mel_encode_batch_dev -- their
+ * final LayerNorm then stores over NVLink exactly as in the single-process gather. */
+int wb_ipc_alloc(int device, size_t bytes, void** d_ptr, uint8_t* handle64);
+int wb_ipc_open(int device, const uint8_t* handle64, void** d_ptr);
+int wb_ipc_close(int device, void* d_ptr);
+int wb_ipc_free(int device, void* d_ptr);
+/* cudaMemcpy of a device buffer this process can address (e.g. the gather buffer) to the host. */
+int wb_read_device(int device, const void* d_src, void* host_dst, size_t bytes);
+
+/* ---- decoder front half ------------------------------------------------ */
+/* 1 when the .apr file carried decoder tensors (load_decoder_weights, src/lib.rs:843-929) and the decode entry points work. */
+int wb_decoder_available(const wb_model* m);
+/* WhisperApr::decode with DecodingStrategy::Greedy (src/lib.rs:529-598; GreedyDecoder::decode, src/inference/greedy.rs:118-146) for B
+ * chunks side by side: states [B][seq_len][d] f32 (host) are the encoder outputs; the cross-attention K/V are computed once per
+ * chunk (two tensor-core GEMMs per decoder layer; decoder.rs:2276-2296 does it on the first token, :2017-2040 per token), then
+ * Decoder::forward_one (decoder.rs:2125-2172) runs per position with a KV cache, WhisperTokenSuppressor::apply
+ * (src/inference/processors.rs:126-147; timestamps suppressed unless suppress_timestamps == 0) and the first-maximum argmax
+ * (greedy.rs:83-96), all on the device.  A chunk stops after EOT; the call stops when every chunk has, or at max_tokens tokens in
+ * total (initial ones included).  tokens_out [B][max_tokens] (padded with EOT), lens_out [B]. */
+int wb_decode_greedy(const wb_model* m, const float* states, size_t seq_len, int B, const int32_t* initial_tokens, int n_init,
+                     int max_tokens, int suppress_timestamps, int32_t* tokens_out, int32_t* lens_out);
+/* transcribe_batch_optimized steps 1-3 up to token ids (src/lib.rs:1162-1201): mel + encoder + greedy decode with the encoder
+ * states never leaving HBM (bf16), sharded over the handle's devices like wb_mel_encode_batch -- the decoder is sharded the same way,
+ * so no gather is needed.  Only token ids come back. */
+int wb_transcribe_tokens_batch(const wb_model* m, const float* const* audio, const size_t* n_samples, int B,
+                               const int32_t* initial_tokens, int n_init, int max_tokens, int suppress_timestamps, int32_t* tokens_out,
+                               int32_t* lens_out);
 
 /* ---- chunking --------------------------------------------------------------------- */
 /* audio::split_into_chunks (src/audio/batch.rs:219-240).  Writes up to `capacity` (start,len)
@@ -170,6 +224,10 @@ int wb_debug_encode(const wb_model* m, const float* mel, size_t mel_len, int n_l
  * {0 mel_stft, 1 mel_finalize, 2 gemm, 3 attention, 4 layernorm, 5 other} and clears the record. */
 int wb_profile_enable(wb_model* m, int on);
 int wb_profile_read(wb_model* m, float* ms_by_cat, int* launches_by_cat, int n_cat);
+/* Decoder test hooks: logits [n_vocab] of Decoder::forward_one after feeding `tokens` (before suppression) for one chunk's states
+ * [seq_len][d]; and K, V ([seq_len][d] f32 each) of one decoder layer's cross-attention. */
+int wb_debug_decoder_logits(const wb_model* m, const float* states, size_t seq_len, const int32_t* tokens, int n_tokens, float* logits_out);
+int wb_debug_cross_kv(const wb_model* m, const float* states, size_t seq_len, int layer, float* k_out, float* v_out);
 /* Number of CUDA kernels this library has launched in this process (all models). */
 long long wb_launch_count(void);
 /* Payload bytes AprReader::load_tensor would read for `name` (src/format/mod.rs:610-628): >= 0, -1 when the tensor is absent or its

@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 
 ENC_TOL, ENC_COS = 2e-2, 0.9999
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-RECORD = os.path.join(ROOT, "gpurun_out", "parity_depth.json")
+RECORD = os.path.join(ROOT, "gpurun_out", os.environ.get("WB_PARITY_RECORD", "parity_depth.json"))
 
 
 def _cos(a, b):
@@ -105,8 +105,20 @@ def test_large_v3_full_depth_bf16_batch32():
     for r in growth:
         print(f"[large-v3 depth] after {r['layers']:2d} layers: max-abs {r['max_abs']:.3e} (|x| <= {r['ref_absmax']:.1f}, rel {r['rel']:.2e}) cos {r['cos']:.7f}")
         assert r["cos"] >= ENC_COS and r["rel"] <= 2e-2
+    # the gate is a max over 1.9 M values of an error whose rms is ~4e-3: two more chunks show the spread
+    more = [synth.synth_audio(s) for s in (105, 106)]
+    out_more = model.mel_encode_batch(more)
+    for s, a, o in zip((105, 106), more, out_more):
+        r = E.forward_mel(M.compute_mel(a, synth.load_filterbank(128)), w, ocfg, dtype=np.float32, attention=E.naive_attention)
+        e = np.abs(o - r)
+        res[f"audio{s}"] = {"max_abs": float(e.max()), "rms": float(np.sqrt((e ** 2).mean())), "cos": _cos(o, r)}
+        print(f"[large-v3 audio {s}] max-abs {e.max():.4e} rms {np.sqrt((e ** 2).mean()):.3e} cos {res[f'audio{s}']['cos']:.7f}")
+    e0 = np.abs(out[0] - ref)
+    res["pos0"]["rms"] = float(np.sqrt((e0 ** 2).mean()))
     _record("large-v3 32L bf16 B=32", {"final": res, "depth": growth, "oracle": "numpy float32, naive softmax attention", "oracle_s": round(t_oracle, 1),
                                        "load_s": round(t_load, 1), "gate": {"max_abs": ENC_TOL, "cos": ENC_COS}})
+    for s in (105, 106):
+        assert res[f"audio{s}"]["max_abs"] <= ENC_TOL and res[f"audio{s}"]["cos"] >= ENC_COS, res
     model.close()
 
 

@@ -423,3 +423,68 @@ def test_attention_growing_scores_rescale_path(S):
         got = out[0, :, h * 64:(h + 1) * 64]
         assert np.isfinite(got).all()
         assert np.abs(got - ref).max() <= 2.5e-2 and _cos(got, ref) > 0.9999
+
+
+def test_n_audio_ctx_smaller_than_1500_is_refused_not_overrun(mel0, fb80):
+    """A header with n_audio_ctx < 1500: the fused 30 s paths return the reference's own error (encoder.rs:456-461) instead of
+    writing 1500 positions into buffers sized for the header's context; shorter mels still encode."""
+    cfg = synth.ModelConfig("ctx1000", 0, 80, 1000, 384, 6, 2, 51865, 448, 384, 6, 2)
+    tensors = [(n, a if n != "encoder.positional_embedding" else a[:1000]) for n, a in synth.random_encoder_tensors(synth.CONFIGS["tiny"], 0)
+               if "layers.2" not in n and "layers.3" not in n]
+    from whisper_apr_b200.apr_writer import write_apr
+    model = WhisperApr.load_from_apr(write_apr(cfg, tensors, 0, fb80))
+    assert model.config.n_audio_ctx == 1000
+    with pytest.raises(WhisperError) as e:
+        model.mel_encode_batch([synth.synth_audio(0)])
+    assert e.value.kind == "Model" and "sequence length 1500 exceeds max 1000" in str(e.value)
+    with pytest.raises(WhisperError) as e:
+        model.encode(mel0[:2002])                                               # 1001 positions
+    assert "exceeds max 1000" in str(e.value)
+    got = model.encode(mel0[:2000])
+    ocfg = E.ModelConfig("ctx1000", 0, 80, 1000, 384, 6, 2)
+    ref = E.forward_mel(mel0[:2000], dict(tensors), ocfg, attention=E.naive_attention)
+    assert got.shape == ref.shape == (1000, 384)
+    assert np.abs(got - ref).max() <= ENC_TOL and _cos(got, ref) >= ENC_COS
+    model.close()
+
+
+def test_per_channel_int8_requantisation(mel0):
+    """quantize_f32_to_i8_per_channel / dequantize_i8_to_f32_per_channel (src/model/quantized.rs:1769-1813) on the device: one scale per
+    output channel of every linear weight, int8 rows resident in HBM, scale applied per output column in the GEMM epilogue."""
+    cfg = synth.CONFIGS["tiny"]
+    data, tensors = synth.random_model_apr(cfg, seed=0)
+    model = WhisperApr.load_from_apr(data)
+    model.requantize_int8_per_channel()
+    w = dict(tensors)
+    for name in list(w):
+        if name.endswith("_proj.weight") or name.endswith("fc1.weight") or name.endswith("fc2.weight"):
+            # the device quantises the bf16-rounded weights it holds
+            a = _bf16_round(w[name]).astype(np.float32)
+            absmax = np.abs(a).max(axis=1, keepdims=True)
+            scale = np.where(absmax < 1e-10, np.float32(1.0), absmax / np.float32(127.0)).astype(np.float32)
+            q = np.clip(np.sign(a / scale) * np.floor(np.abs(a / scale) + np.float32(0.5)), -128, 127)
+            w[name] = (q * scale).astype(np.float32)
+    got = model.encode(mel0[:1000])
+    ref = E.forward_mel(mel0[:1000], w, E.CONFIGS["tiny"], attention=E.naive_attention)
+    assert np.abs(got - ref).max() <= ENC_TOL and _cos(got, ref) >= ENC_COS
+    plain = E.forward_mel(mel0[:1000], dict(tensors), E.CONFIGS["tiny"], attention=E.naive_attention)
+    assert np.abs(got - plain).max() > np.abs(got - ref).max()                  # it really runs the quantised weights
+    with pytest.raises(WhisperError):
+        model.requantize_int8_per_channel()                                     # already quantised
+    model.close()
+
+
+@pytest.mark.parametrize("M_,N,K", [(300, 1152, 384), (777, 1280, 1280)])
+def test_gemm_fp16_weight_format(M_, N, K):
+    """The B operand of tcgen05.mma kind::f16 may be IEEE fp16 while A stays bf16 (separate format fields of the instruction
+    descriptor): same rate, 8x finer weight rounding.  Result against the exactly-rounded operands."""
+    import torch
+    rng = np.random.default_rng(M_ + N)
+    A = rng.standard_normal((M_, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    out = np.empty((M_, N), np.float32)
+    _lib.check(_lib.lib().wb_debug_gemm(0, _p(A), _p(W), _p(bias), None, M_, N, K, 4 | 0x100, C.c_float(1.0), _p(out)))
+    W16 = torch.from_numpy(W).to(torch.float16).to(torch.float64).numpy()
+    ref = _bf16_round(A).astype(np.float64) @ W16.T + bias
+    assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max() / 4)

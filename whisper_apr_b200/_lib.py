@@ -33,6 +33,21 @@ SIGNATURES = {
     "wb_last_error": (C.c_char_p, []),
     "wb_device_count": (C.c_int, []),
     "wb_model_from_apr": (C.c_int, [_vp, C.c_size_t, C.c_int, C.POINTER(_vp)]),
+    "wb_model_from_apr_devices": (C.c_int, [_vp, C.c_size_t, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "wb_model_n_devices": (C.c_int, [_vp]),
+    "wb_model_device": (C.c_int, [_vp, C.c_int]),
+    "wb_model_requantize": (C.c_int, [_vp, C.c_int]),
+    "wb_mel_encode_gather": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "wb_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_vp), _vp]),
+    "wb_ipc_open": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "wb_ipc_close": (C.c_int, [C.c_int, _vp]),
+    "wb_ipc_free": (C.c_int, [C.c_int, _vp]),
+    "wb_read_device": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
+    "wb_decoder_available": (C.c_int, [_vp]),
+    "wb_decode_greedy": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "wb_transcribe_tokens_batch": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "wb_debug_decoder_logits": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, _vp]),
+    "wb_debug_cross_kv": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp, _vp]),
     "wb_model_config": (C.c_int, [_vp, C.POINTER(WbConfig)]),
     "wb_model_free": (None, [_vp]),
     "wb_model_set_stream": (C.c_int, [_vp, _vp]),

@@ -142,12 +142,28 @@ class WhisperApr:
 
     # -- construction ------------------------------------------------------------------
     @classmethod
-    def load_from_apr(cls, data: bytes, device: int = 0) -> "WhisperApr":
+    def load_from_apr(cls, data: bytes, device: int = 0, devices=None) -> "WhisperApr":
+        """WhisperApr::load_from_apr.  `devices` (a list of CUDA ordinals) replicates the model over several GPUs of this process:
+        the batch entry points then shard their chunks over the list (parallel::configure_thread_pool's successor)."""
         arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
         h = C.c_void_p()
-        st = _lib.lib().wb_model_from_apr(C.c_void_p(arr.ctypes.data if arr.size else 0), arr.size, device, C.byref(h))
+        devs = list(devices) if devices is not None else [device]
+        dev_arr = (C.c_int * len(devs))(*devs)
+        st = _lib.lib().wb_model_from_apr_devices(C.c_void_p(arr.ctypes.data if arr.size else 0), arr.size, dev_arr, len(devs), C.byref(h))
         check(st)
         return cls(h)
+
+    @property
+    def n_devices(self) -> int:
+        return int(_lib.lib().wb_model_n_devices(self._h))
+
+    @property
+    def devices(self) -> list:
+        return [int(_lib.lib().wb_model_device(self._h, i)) for i in range(self.n_devices)]
+
+    def requantize_int8_per_channel(self):
+        """quantize_f32_to_i8_per_channel (src/model/quantized.rs:1769-1794) applied on the device to every linear weight."""
+        check(_lib.lib().wb_model_requantize(self._h, 1))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -217,6 +233,70 @@ class WhisperApr:
         ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in audio_batch])
         lens = (C.c_size_t * B)(*[a.size for a in audio_batch])
         check(_lib.lib().wb_mel_encode_batch_async(self._h, ptrs, lens, B, _ptr(out), WB_F32 if out_dtype == "f32" else WB_BF16))
+
+    def mel_encode_gather(self, audio_batch, gather_index: int = 0, out_dtype: str = "bf16") -> np.ndarray:
+        """The sharded call with all encoder states gathered on ONE device (peer stores over NVLink by the final LayerNorm);
+        returns them read back from that device: [B][1500][d] f32, or raw bf16 bits as uint16."""
+        chunks = [_f32(a).ravel() for a in audio_batch]
+        B = len(chunks)
+        d = self.config.n_audio_state
+        S = (N_FRAMES_30S - 1) // 2 + 1
+        out = np.empty((B, S, d), np.float32 if out_dtype == "f32" else np.uint16)
+        if B == 0:
+            return out
+        ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in chunks])
+        lens = (C.c_size_t * B)(*[c.size for c in chunks])
+        d_states = C.c_void_p()
+        check(_lib.lib().wb_mel_encode_gather(self._h, ptrs, lens, B, WB_F32 if out_dtype == "f32" else WB_BF16, gather_index, C.byref(d_states)))
+        self.sync()
+        check(_lib.lib().wb_read_device(self.devices[gather_index], d_states, _ptr(out), out.nbytes))
+        return out
+
+    # -- decoder front half (SURVEY 8f-1) ------------------------------------------------------
+    @property
+    def has_decoder(self) -> bool:
+        return bool(_lib.lib().wb_decoder_available(self._h))
+
+    def decode_greedy(self, states, initial_tokens, max_tokens: int, suppress_timestamps: bool = True):
+        """WhisperApr::decode with the greedy strategy for B chunks: states [B][S][d] (or [S][d]) f32 -> list of token lists."""
+        st = _f32(states)
+        if st.ndim == 2:
+            st = st[None]
+        B, S, _ = st.shape
+        init = np.ascontiguousarray(initial_tokens, np.int32)
+        toks = np.empty((B, max_tokens), np.int32)
+        lens = np.empty(B, np.int32)
+        check(_lib.lib().wb_decode_greedy(self._h, _ptr(st), S, B, _ptr(init), init.size, max_tokens, int(suppress_timestamps), _ptr(toks), _ptr(lens)))
+        return [toks[b, : lens[b]].tolist() for b in range(B)]
+
+    def transcribe_tokens_batch(self, audio_batch, initial_tokens, max_tokens: int, suppress_timestamps: bool = True):
+        """transcribe_batch_optimized up to token ids: mel + encoder + greedy decode, states never leave HBM."""
+        chunks = [_f32(a).ravel() for a in audio_batch]
+        B = len(chunks)
+        if B == 0:
+            return []
+        ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in chunks])
+        lens_in = (C.c_size_t * B)(*[c.size for c in chunks])
+        init = np.ascontiguousarray(initial_tokens, np.int32)
+        toks = np.empty((B, max_tokens), np.int32)
+        lens = np.empty(B, np.int32)
+        check(_lib.lib().wb_transcribe_tokens_batch(self._h, ptrs, lens_in, B, _ptr(init), init.size, max_tokens, int(suppress_timestamps),
+                                                     _ptr(toks), _ptr(lens)))
+        return [toks[b, : lens[b]].tolist() for b in range(B)]
+
+    def debug_decoder_logits(self, states, tokens) -> np.ndarray:
+        st = _f32(states)
+        tk = np.ascontiguousarray(tokens, np.int32)
+        out = np.empty(self.config.n_vocab, np.float32)
+        check(_lib.lib().wb_debug_decoder_logits(self._h, _ptr(st), st.shape[0], _ptr(tk), tk.size, _ptr(out)))
+        return out
+
+    def debug_cross_kv(self, states, layer: int):
+        st = _f32(states)
+        k = np.empty_like(st)
+        v = np.empty_like(st)
+        check(_lib.lib().wb_debug_cross_kv(self._h, _ptr(st), st.shape[0], layer, _ptr(k), _ptr(v)))
+        return k, v
 
     # -- device-pointer entry points (inputs already in HBM) ------------------------------
     def mel_encode_batch_dev(self, d_audio_ptr: int, B: int, d_out_ptr: int, out_dtype: str = "f32"):

@@ -1,0 +1,243 @@
+// Test hooks and measurement helpers of the C ABI (not part of the reference surface): single-kernel entry points for the parity
+// tests, per-kernel event timing for bench.py's roofline, kernel micro-benchmarks for tuning.
+#include "model.h"
+
+using namespace wb;
+
+static inline Replica* rep0(const wb_model* h) { return (h && !h->reps.empty()) ? h->reps[0] : nullptr; }
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------- test hooks
+static int debug_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return set_error(WB_ERR_CUDA, "no CUDA device: libwhisper_b200 has no CPU fallback");
+  }
+  WB_CUDA_OK(cudaSetDevice(device));
+  return WB_OK;
+}
+
+int wb_debug_gemm(int device, const float* A, const float* W, const float* bias, const float* resid_or_pe, int M, int N, int K,
+                  int epilogue, float alpha, float* out) {
+  int rc = debug_device(device);
+  if (rc != WB_OK) return rc;
+  DevBuf<float> fa, fw, fb, fo, fpe;
+  DevBuf<bf16> ba, bw, bo;
+  auto cleanup = [&](int r) { fa.release(); fw.release(); fb.release(); fo.release(); fpe.release(); ba.release(); bw.release(); bo.release(); return r; };
+  const size_t na = static_cast<size_t>(M) * K, nw = static_cast<size_t>(N) * K, no = static_cast<size_t>(M) * N;
+  if ((rc = fa.ensure(na)) || (rc = fw.ensure(nw)) || (rc = fo.ensure(no)) || (rc = ba.ensure(na)) || (rc = bw.ensure(nw)) ||
+      (rc = bo.ensure(no)) || (rc = fb.ensure(N)) || (rc = fpe.ensure(no)))
+    return cleanup(rc);
+  cudaMemcpy(fa.p, A, na * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(fw.p, W, nw * 4, cudaMemcpyHostToDevice);
+  if (bias) cudaMemcpy(fb.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice);
+  const int w_fp16 = (epilogue & 0x100) ? 1 : 0;            // test switch: W held as IEEE fp16 (B format of the MMA descriptor)
+  epilogue &= 0xff;
+  launch_f32_to_bf16(fa.p, ba.p, na, nullptr);
+  launch_f32_to_w16(fw.p, bw.p, nw, w_fp16, nullptr);
+  GemmDesc g{};
+  g.w_fp16 = w_fp16;
+  g.A = ba.p; g.a_row_stride = K; g.a_batch_stride = static_cast<long long>(M) * K; g.rows_per_batch = M; g.n_batch = 1;
+  g.W = bw.p; g.N = N; g.K = K; g.epilogue = epilogue; g.alpha = alpha; g.col_scale = nullptr; g.bias = bias ? fb.p : nullptr;
+  g.ldc = N; g.out_rows_per_batch = M; g.out_row_off = 0; g.pe = nullptr;
+  const bool bf_out = epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16;
+  if (epilogue == EPI_RESID_F32) {
+    if (!resid_or_pe) return cleanup(set_error(WB_ERR_MODEL, "residual input required"));
+    cudaMemcpy(fo.p, resid_or_pe, no * 4, cudaMemcpyHostToDevice);
+  } else if (epilogue == EPI_GELU_PE_F32) {
+    if (!resid_or_pe) return cleanup(set_error(WB_ERR_MODEL, "pe input required"));
+    cudaMemcpy(fpe.p, resid_or_pe, no * 4, cudaMemcpyHostToDevice);
+    g.pe = fpe.p;
+  }
+  g.out = bf_out ? static_cast<void*>(bo.p) : static_cast<void*>(fo.p);
+  if ((rc = launch_gemm(g, nullptr)) != WB_OK) return cleanup(rc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("gemm kernel failed: ") + cudaGetErrorString(e)));
+  if (bf_out) {
+    std::vector<bf16> h(no);
+    cudaMemcpy(h.data(), bo.p, no * 2, cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < no; ++i) out[i] = __bfloat162float(h[i]);
+  } else {
+    cudaMemcpy(out, fo.p, no * 4, cudaMemcpyDeviceToHost);
+  }
+  return cleanup(WB_OK);
+}
+
+int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_heads, float* out) {
+  int rc = debug_device(device);
+  if (rc != WB_OK) return rc;
+  DevBuf<float> f;
+  DevBuf<bf16> bq, bo;
+  auto cleanup = [&](int r) { f.release(); bq.release(); bo.release(); return r; };
+  const size_t nq = static_cast<size_t>(B) * S * 3 * d, no = static_cast<size_t>(B) * S * d;
+  if ((rc = f.ensure(nq)) || (rc = bq.ensure(nq)) || (rc = bo.ensure(no))) return cleanup(rc);
+  cudaMemcpy(f.p, qkv, nq * 4, cudaMemcpyHostToDevice);
+  launch_f32_to_bf16(f.p, bq.p, nq, nullptr);
+  if ((rc = launch_attention(bq.p, bo.p, B, S, d, n_heads, nullptr)) != WB_OK) return cleanup(rc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("attention kernel failed: ") + cudaGetErrorString(e)));
+  std::vector<bf16> h(no);
+  cudaMemcpy(h.data(), bo.p, no * 2, cudaMemcpyDeviceToHost);
+  for (size_t i = 0; i < no; ++i) out[i] = __bfloat162float(h[i]);
+  return cleanup(WB_OK);
+}
+
+int wb_debug_gemm_bench(int device, int n_batch, int rows, int N, int K, int epilogue, int iters, float* ms_per_launch) {
+  int rc = debug_device(device);
+  if (rc != WB_OK) return rc;
+  if (!ms_per_launch || iters <= 0) return set_error(WB_ERR_MODEL, "bad argument");
+  DevBuf<float> f, fb, fo;
+  DevBuf<bf16> ba, bw, bo;
+  auto cleanup = [&](int r) { f.release(); fb.release(); fo.release(); ba.release(); bw.release(); bo.release(); return r; };
+  const size_t M = static_cast<size_t>(n_batch) * rows, na = M * K, nw = static_cast<size_t>(N) * K, no = M * N;
+  const size_t nf = std::max(static_cast<size_t>(rows) * K, nw);
+  const bool bf_out = epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16;
+  if ((rc = f.ensure(nf)) || (rc = fb.ensure(N)) || (rc = ba.ensure(na)) || (rc = bw.ensure(nw)) ||
+      (rc = bf_out ? bo.ensure(no) : fo.ensure(no)))
+    return cleanup(rc);
+  std::vector<float> h(nf);
+  uint32_t x = 777u;
+  for (size_t i = 0; i < nf; ++i) {
+    x = x * 1664525u + 1013904223u;
+    h[i] = (static_cast<float>(x >> 8) / 8388608.0f - 1.0f) * 0.05f;
+  }
+  cudaMemcpy(f.p, h.data(), nf * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(fb.p, h.data(), static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice);
+  launch_f32_to_bf16(f.p, bw.p, nw, nullptr);
+  launch_f32_to_bf16(f.p, ba.p, static_cast<size_t>(rows) * K, nullptr);
+  for (int b = 1; b < n_batch; ++b)
+    cudaMemcpyAsync(ba.p + static_cast<size_t>(b) * rows * K, ba.p, static_cast<size_t>(rows) * K * 2, cudaMemcpyDeviceToDevice, nullptr);
+  if (!bf_out) cudaMemsetAsync(fo.p, 0, no * 4, nullptr);
+  GemmDesc g{};
+  g.A = ba.p; g.a_row_stride = K; g.a_batch_stride = static_cast<long long>(rows) * K; g.rows_per_batch = rows; g.n_batch = n_batch;
+  g.W = bw.p; g.N = N; g.K = K; g.epilogue = epilogue; g.alpha = 1.0f; g.col_scale = nullptr; g.bias = fb.p;
+  g.ldc = N; g.out_rows_per_batch = rows; g.out_row_off = 0; g.pe = nullptr;
+  g.out = bf_out ? static_cast<void*>(bo.p) : static_cast<void*>(fo.p);
+  if (epilogue == EPI_GELU_PE_F32) return cleanup(set_error(WB_ERR_MODEL, "pe epilogue not benchmarked"));
+  EventPair ev;
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
+  if (!e0 || !e1) return cleanup(set_error(WB_ERR_CUDA, "cudaEventCreate failed"));
+  for (int i = 0; i < 2; ++i)
+    if ((rc = launch_gemm(g, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e0, nullptr);
+  for (int i = 0; i < iters; ++i)
+    if ((rc = launch_gemm(g, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e1, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("gemm kernel failed: ") + cudaGetErrorString(e)));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_per_launch = ms / iters;
+  return cleanup(WB_OK);
+}
+
+int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int iters, float* ms_per_launch) {
+  int rc = debug_device(device);
+  if (rc != WB_OK) return rc;
+  if (!ms_per_launch || iters <= 0) return set_error(WB_ERR_MODEL, "bad argument");
+  DevBuf<float> f;
+  DevBuf<bf16> bq, bo;
+  auto cleanup = [&](int r) { f.release(); bq.release(); bo.release(); return r; };
+  const size_t per = static_cast<size_t>(S) * 3 * d, nq = per * B, no = static_cast<size_t>(B) * S * d;
+  if ((rc = f.ensure(per)) || (rc = bq.ensure(nq)) || (rc = bo.ensure(no))) return cleanup(rc);
+  std::vector<float> h(per);
+  uint32_t x = 12345u;
+  for (size_t i = 0; i < per; ++i) {                      // LCG noise in [-2, 2): scores with a realistic spread
+    x = x * 1664525u + 1013904223u;
+    h[i] = (static_cast<float>(x >> 8) / 8388608.0f - 1.0f) * 2.0f;
+  }
+  cudaMemcpy(f.p, h.data(), per * 4, cudaMemcpyHostToDevice);
+  launch_f32_to_bf16(f.p, bq.p, per, nullptr);
+  for (int b = 1; b < B; ++b) cudaMemcpyAsync(bq.p + b * per, bq.p, per * 2, cudaMemcpyDeviceToDevice, nullptr);
+  EventPair ev;
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
+  if (!e0 || !e1) return cleanup(set_error(WB_ERR_CUDA, "cudaEventCreate failed"));
+  for (int i = 0; i < 2; ++i)
+    if ((rc = launch_attention(bq.p, bo.p, B, S, d, n_heads, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e0, nullptr);
+  for (int i = 0; i < iters; ++i)
+    if ((rc = launch_attention(bq.p, bo.p, B, S, d, n_heads, nullptr)) != WB_OK) return cleanup(rc);
+  cudaEventRecord(e1, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("attention kernel failed: ") + cudaGetErrorString(e)));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_per_launch = ms / iters;
+  return cleanup(WB_OK);
+}
+
+long long wb_launch_count(void) { return wb::g_launch_count.load(); }
+
+long long wb_debug_apr_tensor_bytes(const uint8_t* bytes, size_t n_bytes, const char* name) {
+  AprFile f;
+  if (!name || parse_apr(bytes, n_bytes, &f) != WB_OK) return -2;
+  const AprTensor* t = f.find(name);
+  if (!t) return -1;
+  size_t nb = 0;
+  return f.payload(*t, &nb) ? static_cast<long long>(nb) : -1;      // -1: "tensor data out of bounds" (format/mod.rs:610-628)
+}
+
+int wb_profile_enable(wb_model* h, int on) {
+  Replica* m = rep0(h);
+  if (!m) return set_error(WB_ERR_MODEL, "null model");
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->prof_on = on != 0;
+  return WB_OK;
+}
+
+int wb_profile_read(wb_model* h, float* ms_by_cat, int* launches_by_cat, int n_cat) {
+  Replica* m = rep0(h);
+  if (!m || !ms_by_cat || !launches_by_cat) return set_error(WB_ERR_MODEL, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  DeviceGuard guard(m->device);
+  WB_CUDA_OK(cudaStreamSynchronize(m->stream));
+  for (int i = 0; i < n_cat; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
+  for (size_t i = 0; i < m->prof_cat.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]);
+    const int c = m->prof_cat[i];
+    if (c < n_cat) { ms_by_cat[c] += ms; launches_by_cat[c] += 1; }
+  }
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  m->prof_ev.clear();
+  m->prof_cat.clear();
+  return WB_OK;
+}
+
+int wb_debug_encode(const wb_model* h, const float* mel, size_t mel_len, int n_layers, int ln_post, float* out, size_t out_capacity) {
+  Replica* m = rep0(h);
+  if (!m) return set_error(WB_ERR_MODEL, "null model");
+  int rc = check_encoder_dims(m);
+  if (rc != WB_OK) return rc;
+  int T = 0;
+  if ((rc = validate_mel_len(m, mel_len, &T)) != WB_OK) return rc;
+  if (T == 0) return WB_OK;
+  const size_t S = (T - 1) / 2 + 1;
+  if (!mel || !out || out_capacity < S * m->cfg.n_audio_state) return set_error(WB_ERR_MODEL, "output buffer too small");
+  std::lock_guard<std::mutex> lk(m->mu);
+  DeviceGuard guard(m->device);
+  const float* ptrs[1] = {mel};
+  return encode_same_len(m, ptrs, nullptr, 1, T, out, nullptr, S * m->cfg.n_audio_state, WB_F32, n_layers, ln_post != 0);
+}
+
+int wb_debug_layernorm(int device, const float* x, const float* gamma, const float* beta, int rows, int d, float* out) {
+  int rc = debug_device(device);
+  if (rc != WB_OK) return rc;
+  DevBuf<float> fx, fg, fb, fo;
+  auto cleanup = [&](int r) { fx.release(); fg.release(); fb.release(); fo.release(); return r; };
+  const size_t n = static_cast<size_t>(rows) * d;
+  if ((rc = fx.ensure(n)) || (rc = fg.ensure(d)) || (rc = fb.ensure(d)) || (rc = fo.ensure(n))) return cleanup(rc);
+  cudaMemcpy(fx.p, x, n * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(fg.p, gamma, static_cast<size_t>(d) * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(fb.p, beta, static_cast<size_t>(d) * 4, cudaMemcpyHostToDevice);
+  if ((rc = launch_layernorm(fx.p, fg.p, fb.p, rows, d, nullptr, fo.p, nullptr)) != WB_OK) return cleanup(rc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("layernorm kernel failed: ") + cudaGetErrorString(e)));
+  cudaMemcpy(out, fo.p, n * 4, cudaMemcpyDeviceToHost);
+  return cleanup(WB_OK);
+}
+
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// The device pipeline of one replica: workspace, the mel and encoder launch sequences, the fused step (CUDA-graph replay) and the
+// copy/compute overlapped micro-batch queue behind the host-buffer entry points.
+//
+// Mirrors, for the mel + encoder path only:
+//   WhisperApr::{compute_mel, encode}                        src/lib.rs:407-449
+//   Encoder::{forward, forward_mel, forward_batch{,_padded}} src/model/encoder.rs:450-478, 566-660
+//   EncoderBlock::forward                                    src/model/encoder.rs:346-361
+//   transcribe_batch_optimized steps 1-2                     src/lib.rs:1162-1170
+//   BatchPreprocessor::process_batch                         src/audio/batch.rs:157-176
+#include "model.h"
+
+namespace wb {
+
+// ---- workspace ---------------------------------------------------------------------------------
+int ensure_workspace(Replica* m, int B) {
+  Workspace& w = m->ws;
+  if (B <= w.cap) return WB_OK;
+  // a mel of T frames gives S = (T - 1) / 2 + 1 <= n_audio_ctx positions (validate_mel_len), so T <= 2 * ctx; the fused paths
+  // always run T = 3000 / S = 1500 and are refused up front when the header's n_audio_ctx is smaller (check_fused_dims)
+  const size_t d = m->cfg.n_audio_state, nm = std::max<size_t>(m->cfg.n_mels, m->mel.n_mels);
+  const size_t S = std::max<size_t>(m->cfg.n_audio_ctx, (N_FRAMES_30S - 1) / 2 + 1);
+  const size_t T = std::max<size_t>(N_FRAMES_30S, 2 * static_cast<size_t>(m->cfg.n_audio_ctx)), b = static_cast<size_t>(B);
+  int rc;
+  if ((rc = w.audio.ensure(b * N_SAMPLES_30S)) != WB_OK) return rc;
+  if ((rc = w.n_valid.ensure(b)) != WB_OK) return rc;
+  if ((rc = w.max_key.ensure(b)) != WB_OK) return rc;
+  if ((rc = w.logmel.ensure(b * T * nm)) != WB_OK) return rc;
+  if ((rc = w.mel_f32.ensure(b * T * nm)) != WB_OK) return rc;
+  if ((rc = w.mel_bf16.ensure(b * (T + 2) * nm)) != WB_OK) return rc;
+  if ((rc = w.c1.ensure(b * (T + 2) * d)) != WB_OK) return rc;
+  if ((rc = w.x.ensure(b * S * d)) != WB_OK) return rc;
+  if ((rc = w.xn.ensure(b * S * d)) != WB_OK) return rc;
+  if ((rc = w.qkv.ensure(b * S * 3 * d)) != WB_OK) return rc;
+  if ((rc = w.att.ensure(b * S * d)) != WB_OK) return rc;
+  if ((rc = w.hid.ensure(b * S * 4 * d)) != WB_OK) return rc;
+  if ((rc = w.out_f32.ensure(b * S * d)) != WB_OK) return rc;
+  if ((rc = w.out_bf16.ensure(b * S * d)) != WB_OK) return rc;
+  w.cap = B;
+  for (auto& g : m->graphs)                 // workspace pointers are baked into captured launches
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
+  return WB_OK;
+}
+
+// ---- encoder launch sequence ------------------------------------------------------------------------
+// Precondition: ws.mel_bf16 holds [B][T+2][n_mels] bf16 with rows 1..T = mel frames and zero guard rows.
+// d_out: [B][S][d] f32 or bf16 (device).  n_layers < 0 -> all layers; ln_post as Encoder::forward (encoder.rs:477).
+int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int n_layers, bool ln_post) {
+  const int d = static_cast<int>(m->cfg.n_audio_state), nm = static_cast<int>(m->cfg.n_mels);
+  const int H = static_cast<int>(m->cfg.n_audio_head);
+  const int S = (T - 1) / 2 + 1;               // conv2: (T + 2 - 3) / 2 + 1 (encoder.rs:79)
+  Workspace& w = m->ws;
+  cudaStream_t st = m->stream;
+  int rc;
+  NvtxRange nvtx("step_g_encode");            // the reference's renacer span of the encoder stage (.renacer.toml:11-32)
+  const int L = n_layers < 0 ? static_cast<int>(m->layers.size()) : std::min<int>(n_layers, static_cast<int>(m->layers.size()));
+
+  // c1 guard rows (0 and T+1) are zero: conv2's padding
+  WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.c1.p, static_cast<long long>(T + 2) * d, B, d, st));
+  WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.c1.p + static_cast<long long>(T + 1) * d, static_cast<long long>(T + 2) * d, B, d, st));
+
+  GemmDesc g{};
+  g.w_fp16 = m->w_fp16;
+  // conv1 + GELU: row t of the operand = padded frames t, t+1, t+2 (3*nm contiguous values)
+  g.A = w.mel_bf16.p; g.a_row_stride = nm; g.a_batch_stride = static_cast<long long>(T + 2) * nm;
+  g.rows_per_batch = T; g.n_batch = B;
+  g.W = m->conv1_w; g.N = d; g.K = 3 * nm;
+  g.epilogue = EPI_GELU_BF16; g.alpha = m->conv1_s; g.col_scale = nullptr; g.bias = m->conv1_b;
+  g.out = w.c1.p; g.ldc = d; g.out_rows_per_batch = T + 2; g.out_row_off = 1; g.pe = nullptr;
+  WB_PROF(PC_GEMM, launch_gemm(g, st));
+  // conv2 (stride 2) + GELU + positional embedding -> fp32 residual stream
+  g.A = w.c1.p; g.a_row_stride = 2LL * d; g.a_batch_stride = static_cast<long long>(T + 2) * d;
+  g.rows_per_batch = S; g.n_batch = B;
+  g.W = m->conv2_w; g.N = d; g.K = 3 * d;
+  g.epilogue = EPI_GELU_PE_F32; g.alpha = m->conv2_s; g.bias = m->conv2_b;
+  g.out = w.x.p; g.ldc = d; g.out_rows_per_batch = S; g.out_row_off = 0; g.pe = m->pe;
+  WB_PROF(PC_GEMM, launch_gemm(g, st));
+
+  const int M = B * S;
+  auto flat = [&](const bf16* A, int K, const bf16* W, int N, int epi, float alpha, const float* cs, const float* bias, void* out) {
+    GemmDesc q{};
+    q.w_fp16 = m->w_fp16;
+    q.A = A; q.a_row_stride = K; q.a_batch_stride = static_cast<long long>(M) * K; q.rows_per_batch = M; q.n_batch = 1;
+    q.W = W; q.N = N; q.K = K; q.epilogue = epi; q.alpha = alpha; q.col_scale = cs; q.bias = bias;
+    q.out = out; q.ldc = N; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
+    return launch_gemm(q, st);
+  };
+  // Quantised models: a layer's packed weights are expanded to bf16 (exact integer values; the scale stays in the GEMM epilogue)
+  // right before the GEMM that consumes them, into buffers every layer reuses.  With M = B x 1500 rows per launch each weight tile
+  // is consumed by ~190 row tiles, so expanding once per launch costs 1/190th of converting inside every CTA, and the 12 d^2
+  // bf16 (39 MB for d = 1280) stay L2-resident for the GEMM that follows; HBM only ever holds the packed bytes.
+  const size_t dd = static_cast<size_t>(d) * d;
+  auto expand = [&](const uint8_t* packed, bf16* dst, size_t n) {
+    return m->quant == 2 ? launch_i8_to_w16(reinterpret_cast<const int8_t*>(packed), dst, n, m->w_fp16, st) : launch_i4_to_w16(packed, dst, n, m->w_fp16, st);
+  };
+  for (int i = 0; i < L; ++i) {
+    const LayerW& lw = m->layers[i];
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, nullptr, st));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.pqkv, lw.wqkv, 3 * dd)); }
+    WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p));
+    WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.po, lw.wo, dd)); }
+    WB_PROF(PC_GEMM, flat(w.att.p, d, lw.wo, d, EPI_RESID_F32, lw.so, lw.cso, lw.bo, w.x.p));
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln2_g, lw.ln2_b, M, d, w.xn.p, nullptr, st));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p1, lw.w1, 4 * dd)); }
+    WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.w1, 4 * d, EPI_GELU_BF16, lw.s1, lw.cs1, lw.b1, w.hid.p));
+    if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p2, lw.w2, 4 * dd)); }
+    WB_PROF(PC_GEMM, flat(w.hid.p, 4 * d, lw.w2, d, EPI_RESID_F32, lw.s2, lw.cs2, lw.b2, w.x.p));
+  }
+  if (ln_post) {
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, m->lnp_g, m->lnp_b, M, d, out_dtype == WB_BF16 ? static_cast<bf16*>(d_out) : nullptr,
+                                           out_dtype == WB_BF16 ? nullptr : static_cast<float*>(d_out), st));
+  } else {
+    if (out_dtype == WB_BF16) rc = launch_f32_to_bf16(w.x.p, static_cast<bf16*>(d_out), static_cast<size_t>(M) * d, st);
+    else {
+      WB_CUDA_OK(cudaMemcpyAsync(d_out, w.x.p, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (rc != WB_OK) return rc;
+  }
+  return WB_OK;
+}
+
+// mel of B chunks already in ws.audio ([B][480000], n_valid per chunk in ws.n_valid) -> optional f32 [B][3000][m] and/or
+// the bf16 padded operand in ws.mel_bf16.
+int mel_device(Replica* m, const float* d_audio, const int* d_n_valid, int B, float* d_mel_f32, bool want_bf16) {
+  Workspace& w = m->ws;
+  const int nm = m->mel.n_mels;
+  const int n_frames = (N_SAMPLES_30S - N_FFT) / HOP + 1;     // 2998 (mel.rs:245-249)
+  int rc;
+  NvtxRange nvtx("step_f_mel");               // the reference's span name for MelFilterbank::compute (src/audio/mel.rs:234)
+  WB_PROF(PC_MEL_STFT, launch_mel_stft(d_audio, N_SAMPLES_30S, d_n_valid, N_SAMPLES_30S, HOP, n_frames, B, m->mel, w.logmel.p,
+                                       w.max_key.p, m->stream));
+  if (want_bf16) {
+    const long long bs = static_cast<long long>(N_FRAMES_30S + 2) * nm;
+    WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.mel_bf16.p, bs, B, nm, m->stream));
+    WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.mel_bf16.p + static_cast<long long>(N_FRAMES_30S + 1) * nm, bs, B, nm, m->stream));
+  }
+  WB_PROF(PC_MEL_FINALIZE, launch_mel_finalize(w.logmel.p, w.max_key.p, n_frames, N_FRAMES_30S, nm, B, d_mel_f32,
+                                               want_bf16 ? w.mel_bf16.p : nullptr, m->stream));
+  return WB_OK;
+}
+
+int check_encoder_dims(const Replica* m) {
+  const wb_config& c = m->cfg;
+  if (c.n_audio_state == 0 || c.n_audio_state % 128 != 0 || c.n_audio_head == 0 || c.n_audio_state != c.n_audio_head * 64)
+    return set_error(WB_ERR_MODEL, "encoder kernels need n_audio_state % 128 == 0 and d_head == 64");
+  if (c.n_mels == 0 || c.n_mels % 8 != 0) return set_error(WB_ERR_MODEL, "encoder kernels need n_mels % 8 == 0");
+  if (static_cast<int>(c.n_mels) != m->mel.n_mels)
+    return set_error(WB_ERR_MODEL, "filterbank n_mels differs from the model's n_mels");
+  return WB_OK;
+}
+
+// The fused 30 s paths always produce 1500 positions: a header with a smaller n_audio_ctx gets the reference's own error
+// (Encoder::forward, encoder.rs:456-461) instead of a workspace / positional-embedding overrun.
+int check_fused_dims(const Replica* m) {
+  int rc = check_encoder_dims(m);
+  if (rc != WB_OK) return rc;
+  const size_t S = (N_FRAMES_30S - 1) / 2 + 1;
+  if (S > m->cfg.n_audio_ctx)
+    return set_error(WB_ERR_MODEL, "sequence length " + std::to_string(S) + " exceeds max " + std::to_string(m->cfg.n_audio_ctx));
+  return WB_OK;
+}
+
+
+// MelFilterbank::compute for one segment with the given filter tables (host in, host out).  Caller holds the model lock.
+int mel_compute_one(Replica* m, const MelTables& tab, const float* audio, size_t n, size_t hop, float* out, size_t out_capacity,
+                           size_t* n_frames_out) {
+  if (n_frames_out) *n_frames_out = 0;
+  if (n == 0) return WB_OK;                                                        // mel.rs:236-238
+  if (hop == 0) return set_error(WB_ERR_AUDIO, "hop_length must be positive");     // mel.rs:240-242
+  const size_t n_frames = n >= N_FFT ? (n - N_FFT) / hop + 1 : 0;                  // mel.rs:245-249
+  if (n_frames == 0) return WB_OK;
+  const int nm = tab.n_mels;
+  if (n > 0x7fff0000ull || hop > 0x7fff0000ull) return set_error(WB_ERR_AUDIO, "audio too long for one call");
+  if (!audio || !out || out_capacity < n_frames * nm) return set_error(WB_ERR_AUDIO, "output buffer too small");
+  DevBuf<float> d_audio, d_log, d_out;
+  DevBuf<int> d_key;
+  int rc;
+  auto cleanup = [&](int r) { d_audio.release(); d_log.release(); d_out.release(); d_key.release(); return r; };
+  if ((rc = d_audio.ensure((n + 3) & ~static_cast<size_t>(3))) != WB_OK) return cleanup(rc);
+  if ((rc = d_log.ensure(n_frames * nm)) != WB_OK) return cleanup(rc);
+  if ((rc = d_out.ensure(n_frames * nm)) != WB_OK) return cleanup(rc);
+  if ((rc = d_key.ensure(1)) != WB_OK) return cleanup(rc);
+  if (cudaMemcpyAsync(d_audio.p, audio, n * 4, cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
+    return cleanup(set_error(WB_ERR_CUDA, "H2D audio copy failed"));
+  rc = launch_mel_stft(d_audio.p, static_cast<long long>(d_audio.n), nullptr, static_cast<int>(n), static_cast<int>(hop),
+                       static_cast<int>(n_frames), 1, tab, d_log.p, d_key.p, m->stream);
+  if (rc != WB_OK) return cleanup(rc);
+  rc = launch_mel_finalize(d_log.p, d_key.p, static_cast<int>(n_frames), static_cast<int>(n_frames), nm, 1, d_out.p, nullptr, m->stream);
+  if (rc != WB_OK) return cleanup(rc);
+  if (cudaMemcpyAsync(out, d_out.p, n_frames * nm * 4, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess ||
+      cudaStreamSynchronize(m->stream) != cudaSuccess)
+    return cleanup(set_error(WB_ERR_CUDA, std::string("mel kernels failed: ") + cudaGetErrorString(cudaGetLastError())));
+  if (n_frames_out) *n_frames_out = n_frames;
+  return cleanup(WB_OK);
+}
+
+
+int compute_mel_host(Replica* m, const float* const* audio, const size_t* n_samples, const float* contiguous, int B,
+                            float* out) {
+  const int nm = m->mel.n_mels;
+  const size_t per_out = static_cast<size_t>(N_FRAMES_30S) * nm;
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = std::min(m->max_batch, B - b0);
+    int rc = ensure_workspace(m, nb);
+    if (rc != WB_OK) return rc;
+    std::vector<int> nv(nb);
+    for (int i = 0; i < nb; ++i) {
+      const size_t n = contiguous ? N_SAMPLES_30S : std::min<size_t>(n_samples[b0 + i], N_SAMPLES_30S);   // lib.rs:413-425
+      nv[i] = static_cast<int>(n);
+      const float* src = contiguous ? contiguous + static_cast<size_t>(b0 + i) * N_SAMPLES_30S : audio[b0 + i];
+      if (n) WB_CUDA_OK(cudaMemcpyAsync(m->ws.audio.p + static_cast<size_t>(i) * N_SAMPLES_30S, src, n * 4, cudaMemcpyHostToDevice, m->stream));
+    }
+    WB_CUDA_OK(cudaMemcpyAsync(m->ws.n_valid.p, nv.data(), nb * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    if ((rc = mel_device(m, m->ws.audio.p, m->ws.n_valid.p, nb, m->ws.mel_f32.p, false)) != WB_OK) return rc;
+    WB_CUDA_OK(cudaMemcpyAsync(out + static_cast<size_t>(b0) * per_out, m->ws.mel_f32.p, nb * per_out * 4, cudaMemcpyDeviceToHost, m->stream));
+    WB_CUDA_OK(cudaStreamSynchronize(m->stream));     // nv goes out of scope; out is host-visible
+  }
+  return WB_OK;
+}
+
+
+int encode_same_len(Replica* m, const float* const* mels, const float* d_mel, int B, int T, void* out_host, void* out_dev,
+                           size_t out_stride_elems, wb_dtype dt, int n_layers, bool ln_post) {
+  // B mels of T frames each (host pointers `mels` or one device array `d_mel` [B][T][nm]) -> [B][S][d]
+  const int nm = static_cast<int>(m->cfg.n_mels), d = static_cast<int>(m->cfg.n_audio_state);
+  const int S = (T - 1) / 2 + 1;
+  const size_t esz = dt == WB_BF16 ? 2 : 4;
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = std::min(m->max_batch, B - b0);
+    int rc = ensure_workspace(m, nb);
+    if (rc != WB_OK) return rc;
+    const float* src_dev;
+    if (d_mel) {
+      src_dev = d_mel + static_cast<size_t>(b0) * T * nm;
+    } else {
+      for (int i = 0; i < nb; ++i)
+        WB_CUDA_OK(cudaMemcpyAsync(m->ws.mel_f32.p + static_cast<size_t>(i) * T * nm, mels[b0 + i], static_cast<size_t>(T) * nm * 4,
+                                   cudaMemcpyHostToDevice, m->stream));
+      src_dev = m->ws.mel_f32.p;
+    }
+    if ((rc = launch_mel_pad_bf16(src_dev, m->ws.mel_bf16.p, nb, T, nm, m->stream)) != WB_OK) return rc;
+    void* dst_dev;
+    if (out_dev) dst_dev = static_cast<uint8_t*>(out_dev) + static_cast<size_t>(b0) * out_stride_elems * esz;
+    else dst_dev = dt == WB_BF16 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
+    if ((rc = encode_device(m, nb, T, dst_dev, dt, n_layers, ln_post)) != WB_OK) return rc;
+    if (out_host) {
+      const size_t row_bytes = static_cast<size_t>(S) * d * esz;
+      WB_CUDA_OK(cudaMemcpy2DAsync(static_cast<uint8_t*>(out_host) + static_cast<size_t>(b0) * out_stride_elems * esz,
+                                   out_stride_elems * esz, dst_dev, row_bytes, row_bytes, nb, cudaMemcpyDeviceToHost, m->stream));
+      WB_CUDA_OK(cudaStreamSynchronize(m->stream));
+    }
+  }
+  return WB_OK;
+}
+
+int validate_mel_len(const Replica* m, size_t mel_len, int* T_out) {
+  const size_t nm = m->cfg.n_mels;
+  if (mel_len % nm != 0)                                                             // encoder.rs:568-574
+    return set_error(WB_ERR_MODEL, "mel size " + std::to_string(mel_len) + " not divisible by n_mels " + std::to_string(nm));
+  const size_t T = mel_len / nm;
+  const size_t S = T == 0 ? 0 : (T - 1) / 2 + 1;
+  if (S > m->cfg.n_audio_ctx)                                                        // encoder.rs:456-461
+    return set_error(WB_ERR_MODEL, "sequence length " + std::to_string(S) + " exceeds max " + std::to_string(m->cfg.n_audio_ctx));
+  *T_out = static_cast<int>(T);
+  return WB_OK;
+}
+
+
+// One fused mel + encoder step on the model's stream, replayed from a CUDA graph once its (pointers, batch) key has been seen twice.
+int mel_encode_step(Replica* m, const float* d_audio, const int* d_n_valid, int nb, void* d_out, wb_dtype out_dtype) {
+  auto eager = [&]() -> int {
+    int rc = mel_device(m, d_audio, d_n_valid, nb, nullptr, true);
+    if (rc != WB_OK) return rc;
+    return encode_device(m, nb, N_FRAMES_30S, d_out, out_dtype, -1, true);
+  };
+  if (!m->use_graphs || m->prof_on) return eager();
+  Replica::StepGraph* g = nullptr;
+  for (auto& e : m->graphs)
+    if (e.in == d_audio && e.n_valid == d_n_valid && e.out == d_out && e.B == nb && e.dtype == static_cast<int>(out_dtype)) g = &e;
+  if (!g) {
+    if (m->graphs.size() >= 16) {                         // callers that never repeat their pointers do not accumulate graphs
+      for (auto& e : m->graphs)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+      m->graphs.clear();
+    }
+    Replica::StepGraph e;
+    e.in = d_audio; e.n_valid = d_n_valid; e.out = d_out; e.B = nb; e.dtype = static_cast<int>(out_dtype); e.seen = 1;
+    m->graphs.push_back(e);
+    return eager();
+  }
+  if (g->exec) {
+    WB_CUDA_OK(cudaGraphLaunch(g->exec, m->stream));
+    count_launch(static_cast<int>(g->launches));
+    return WB_OK;
+  }
+  // second sighting: capture the launch sequence (thread-local mode: other threads' CUDA calls are unaffected)
+  const long long before = g_launch_count.load();
+  WB_CUDA_OK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = eager();
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+  if (rc != WB_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    m->use_graphs = false;                                // fall back to plain launches for this model
+    if (rc != WB_OK) return rc;
+    return eager();
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    m->use_graphs = false;
+    return eager();
+  }
+  g->exec = exec;
+  g->launches = g_launch_count.load() - before;
+  WB_CUDA_OK(cudaGraphLaunch(exec, m->stream));
+  return WB_OK;
+}
+
+
+int prepare_slot(Replica* m, Replica::Slot& sl, int nb, size_t out_bytes) {
+  int rc;
+  if (!m->in_stream) {
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
+  }
+  if (!sl.in_done) {
+    WB_CUDA_OK(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+    WB_CUDA_OK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+    WB_CUDA_OK(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+  }
+  if (sl.busy) {                                         // the batch that used this slot two calls ago must have left it
+    WB_CUDA_OK(cudaEventSynchronize(sl.out_done));
+    sl.busy = false;
+  }
+  if ((rc = sl.audio.ensure(static_cast<size_t>(nb) * N_SAMPLES_30S)) != WB_OK) return rc;
+  if ((rc = sl.n_valid.ensure(nb)) != WB_OK) return rc;
+  if (out_bytes && (rc = sl.out.ensure(out_bytes)) != WB_OK) return rc;
+  if (sl.h_cap < nb) {
+    if (sl.h_n_valid) cudaFreeHost(sl.h_n_valid);
+    sl.h_n_valid = nullptr;
+    WB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&sl.h_n_valid), static_cast<size_t>(nb) * sizeof(int), cudaHostAllocDefault));
+    sl.h_cap = nb;
+  }
+  return WB_OK;
+}
+
+// transcribe_batch_optimized steps 1-2 from host buffers, one micro-batch: copy-in stream (audio H2D) -> the replica's stream
+// (mel + encoder) -> copy-out stream (states D2H), chained by events over two staging slots.  With d_out_final the final LayerNorm
+// writes the states straight to that address (this device's or, over NVLink, a peer's memory) and nothing is copied out.
+int enqueue_microbatch(Replica* m, const float* const* audio, const size_t* n_samples, int nb, void* out_host, void* d_out_final,
+                       wb_dtype out_dtype) {
+  int rc;
+  const size_t d = m->cfg.n_audio_state, S = N_POS_30S, esz = out_dtype == WB_BF16 ? 2 : 4;
+  const size_t out_bytes = static_cast<size_t>(nb) * S * d * esz;
+  Replica::Slot& sl = m->slot[m->next_slot];
+  m->next_slot ^= 1;
+  if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
+  if ((rc = prepare_slot(m, sl, nb, d_out_final ? 0 : out_bytes)) != WB_OK) return rc;
+  for (int i = 0; i < nb; ++i) {
+    const size_t n = std::min<size_t>(n_samples[i], N_SAMPLES_30S);
+    sl.h_n_valid[i] = static_cast<int>(n);
+    if (n) WB_CUDA_OK(cudaMemcpyAsync(sl.audio.p + static_cast<size_t>(i) * N_SAMPLES_30S, audio[i], n * 4, cudaMemcpyHostToDevice, m->in_stream));
+  }
+  WB_CUDA_OK(cudaMemcpyAsync(sl.n_valid.p, sl.h_n_valid, nb * sizeof(int), cudaMemcpyHostToDevice, m->in_stream));
+  WB_CUDA_OK(cudaEventRecord(sl.in_done, m->in_stream));
+  WB_CUDA_OK(cudaStreamWaitEvent(m->stream, sl.in_done, 0));
+  void* d_out = d_out_final ? d_out_final : static_cast<void*>(sl.out.p);
+  if ((rc = mel_encode_step(m, sl.audio.p, sl.n_valid.p, nb, d_out, out_dtype)) != WB_OK) return rc;
+  WB_CUDA_OK(cudaEventRecord(sl.compute_done, m->stream));
+  if (out_host) {
+    WB_CUDA_OK(cudaStreamWaitEvent(m->out_stream, sl.compute_done, 0));
+    WB_CUDA_OK(cudaMemcpyAsync(out_host, sl.out.p, out_bytes, cudaMemcpyDeviceToHost, m->out_stream));
+    WB_CUDA_OK(cudaEventRecord(sl.out_done, m->out_stream));
+  } else {
+    WB_CUDA_OK(cudaEventRecord(sl.out_done, m->stream));       // the slot's audio buffer is free once the step has run
+  }
+  sl.busy = true;
+  return WB_OK;
+}
+
+int sync_replica(Replica* m) {
+  DeviceGuard guard(m->device);
+  for (auto& sl : m->slot) {
+    if (sl.busy) {
+      WB_CUDA_OK(cudaEventSynchronize(sl.out_done));
+      sl.busy = false;
+    }
+  }
+  WB_CUDA_OK(cudaStreamSynchronize(m->stream));
+  return WB_OK;
+}
+
+// BatchPreprocessor::process_batch (src/audio/batch.rs:157-176) on the device: every segment through MelFilterbank::compute with the
+// given tables, neither padded nor truncated.
+int mel_compute_ragged(Replica* m, const MelTables& tab, const float* const* audio, const size_t* n_samples, int B, size_t hop,
+                       float* const* mels_out, const size_t* out_capacity, size_t* frame_counts, size_t* max_frames_out) {
+  size_t max_frames = 0;
+  for (int i = 0; i < B; ++i) {
+    size_t nf = 0;
+    int rc = mel_compute_one(m, tab, audio[i], n_samples[i], hop, mels_out[i], out_capacity ? out_capacity[i] : 0, &nf);
+    if (rc != WB_OK) return rc;
+    if (frame_counts) frame_counts[i] = nf;
+    max_frames = std::max(max_frames, nf);
+  }
+  if (max_frames_out) *max_frames_out = max_frames;
+  return WB_OK;
+}
+
+}  // namespace wb

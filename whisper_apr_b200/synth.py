@@ -17,7 +17,7 @@ import numpy as np
 
 N_SAMPLES_30S = 480_000
 SAMPLE_RATE = 16_000
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 @dataclass(frozen=True)
@@ -58,8 +58,8 @@ def encoder_gflop_per_chunk(cfg: ModelConfig) -> float:
 
 
 def load_filterbank(n_mels: int) -> np.ndarray:
-    """The slaney filterbank the reference ships (data/mel_{80,128}.bin), committed under tests/golden/."""
-    path = os.path.join(_GOLDEN, f"mel_{n_mels}.bin")
+    """The slaney filterbank tables the reference ships (data/mel_{80,128}.bin; OpenAI's mel_filters.npz rows), kept as package data."""
+    path = os.path.join(_DATA, f"mel_{n_mels}.bin")
     return np.fromfile(path, "<f4").reshape(n_mels, 201).astype(np.float32)
 
 
@@ -125,9 +125,46 @@ def random_encoder_tensors(cfg: ModelConfig, seed: int = 0):
     return out
 
 
-def random_model_apr(cfg: ModelConfig, quant: int = 0, seed: int = 0, with_filterbank: bool = True):
+def random_decoder_tensors(cfg: ModelConfig, seed: int = 1):
+    """Ordered (name, f32 array) list of a random-init decoder, tensor names as load_decoder_weights reads them
+    (src/lib.rs:843-929; k_proj has no bias in Whisper checkpoints).  A strong positional term keeps a random decoder from emitting
+    one token forever, so the greedy sequence varies along the positions and with the audio."""
+    rng = np.random.default_rng(seed)
+    d, L = cfg.n_text_state, cfg.n_text_layer
+    out = [("decoder.embed_tokens.weight", (0.05 * rng.standard_normal((cfg.n_vocab, d))).astype(np.float32)),
+           ("decoder.embed_positions.weight", (0.5 * rng.standard_normal((cfg.n_text_ctx, d))).astype(np.float32))]
+
+    def lin(name, n_out, n_in, bias=True):
+        b = 1.0 / np.sqrt(n_in)
+        out.append((name + ".weight", rng.uniform(-b, b, (n_out, n_in)).astype(np.float32)))
+        if bias:
+            out.append((name + ".bias", (0.02 * rng.standard_normal(n_out)).astype(np.float32)))
+
+    def ln(name):
+        out.append((name + ".weight", (1.0 + 0.02 * rng.standard_normal(d)).astype(np.float32)))
+        out.append((name + ".bias", (0.02 * rng.standard_normal(d)).astype(np.float32)))
+
+    for i in range(L):
+        p = f"decoder.layers.{i}"
+        ln(p + ".self_attn_layer_norm")
+        ln(p + ".encoder_attn_layer_norm")
+        ln(p + ".final_layer_norm")
+        for a in ("self_attn", "encoder_attn"):
+            lin(f"{p}.{a}.q_proj", d, d)
+            lin(f"{p}.{a}.k_proj", d, d, bias=False)
+            lin(f"{p}.{a}.v_proj", d, d)
+            lin(f"{p}.{a}.out_proj", d, d)
+        lin(p + ".fc1", 4 * d, d)
+        lin(p + ".fc2", d, 4 * d)
+    ln("decoder.layer_norm")
+    return out
+
+
+def random_model_apr(cfg: ModelConfig, quant: int = 0, seed: int = 0, with_filterbank: bool = True, with_decoder: bool = False):
     """(apr bytes, tensors list) of a random-init model of the named architecture."""
     from .apr_writer import write_apr
     tensors = random_encoder_tensors(cfg, seed)
+    if with_decoder:
+        tensors = tensors + random_decoder_tensors(cfg, seed + 1)
     fb = load_filterbank(cfg.n_mels) if with_filterbank else None
     return write_apr(cfg, tensors, quant, fb), tensors
