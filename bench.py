@@ -94,25 +94,32 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_sample(cfg_name: str, threads: int):
-    """Bounded sample of the reference's CPU algorithm (oracle/whisper_ref.c port) on one chunk of the bench workload; the
-    per-chunk time is extrapolated by exact op counts.  Returns (audio_s_per_s, description, seconds spent)."""
+    """One bounded sample of the reference's CPU algorithm (oracle/whisper_ref.c, the C restatement of the Rust loops) on one chunk of
+    the bench workload.  Nothing inside a stage is sampled any more: the mel, the WHOLE conv stem (all 3000 frames), ONE COMPLETE
+    encoder layer (LayerNorms, attention over all 1500 positions with `threads` threads over the heads as the reference's rayon
+    feature does, and the scalar FFN over all 1500 rows) and the final LayerNorm are timed as they run; the chunk time is
+    mel + stem + L x layer + ln_post -- the only extrapolation is "L identical layers", stated in the sample string.  whisper-tiny
+    (4 layers) is timed end to end with no multiplication at all.  Returns (audio_s_per_s, description, seconds spent)."""
     from oracle import cref
     from oracle import encoder as E
     from whisper_apr_b200 import synth
     cfg = E.CONFIGS[cfg_name]
     d, L, H, m = cfg.n_audio_state, cfg.n_audio_layer, cfg.n_audio_head, cfg.n_mels
-    rng = np.random.default_rng(0)
     t_all = time.perf_counter()
     audio = synth.synth_audio(0)
     fb = synth.load_filterbank(m)
+    rng = np.random.default_rng(0)
     t0 = time.perf_counter(); mel = cref.compute_mel(audio, fb); t_mel = time.perf_counter() - t0
-    # conv stem on T_s of 3000 frames
-    T_s = 300 if d >= 768 else 3000
+    if L <= 4:                                   # configs[0]: the whole chunk, every layer, as it runs
+        w = dict(synth.random_encoder_tensors(synth.CONFIGS[cfg_name], 0))
+        t0 = time.perf_counter(); cref.forward_mel(mel, w, cfg, threads=threads); t_enc = time.perf_counter() - t0
+        t_chunk = t_mel + t_enc
+        desc = (f"1 complete chunk of {cfg_name}, nothing sampled or extrapolated: mel {t_mel:.2f}s + conv stem, {L} layers and ln_post {t_enc:.2f}s "
+                f"({threads} thread(s) over attention heads)")
+        return CHUNK_SECONDS / t_chunk, desc, time.perf_counter() - t_all
     w = {"encoder.conv1.weight": (rng.standard_normal((d, m, 3)) / np.sqrt(3 * m)).astype(np.float32), "encoder.conv1.bias": np.zeros(d, np.float32),
          "encoder.conv2.weight": (rng.standard_normal((d, d, 3)) / np.sqrt(3 * d)).astype(np.float32), "encoder.conv2.bias": np.zeros(d, np.float32)}
-    t0 = time.perf_counter(); x = cref.conv_stem(mel[:T_s], w, cfg); t_stem = (time.perf_counter() - t0) * (3000.0 / T_s)
-    # one encoder layer: attention (QKV/O via the vectorised matmul, all heads over `threads`) on all 1500 positions,
-    # scalar FFN on R of 1500 rows
+    t0 = time.perf_counter(); x = cref.conv_stem(mel, w, cfg); t_stem = time.perf_counter() - t0
     lw = {}
     p = "encoder.layers.0"
     for k in ("q", "k", "v", "out"):
@@ -123,40 +130,51 @@ def cpu_sample(cfg_name: str, threads: int):
     for n in ("self_attn_layer_norm", "final_layer_norm"):
         lw[f"{p}.{n}.weight"] = np.ones(d, np.float32); lw[f"{p}.{n}.bias"] = np.zeros(d, np.float32)
     W = cref.LayerWeights(lw, 0, d)
-    xs = rng.standard_normal((1500, d)).astype(np.float32)
-    t0 = time.perf_counter(); n1 = cref.layernorm(xs, W.ln1g, W.ln1b); t_ln = time.perf_counter() - t0
-    t0 = time.perf_counter(); cref.mha(n1, W, H, threads=threads); t_att = time.perf_counter() - t0
-    R = 1500 if d <= 384 else max(32, int(1500 * (384.0 / d) ** 2 / 4))
-    t0 = time.perf_counter(); cref.ffn(n1[:R], W); t_ffn = (time.perf_counter() - t0) * (1500.0 / R)
-    t_layer = 2 * t_ln + t_att + t_ffn
+    t0 = time.perf_counter(); x = cref.encoder_layer(x, W, H, threads=threads); t_layer = time.perf_counter() - t0
+    t0 = time.perf_counter(); cref.layernorm(x, W.ln1g, W.ln1b); t_ln = time.perf_counter() - t0
     t_chunk = t_mel + t_stem + L * t_layer + t_ln
-    desc = (f"1 chunk of {cfg_name}: mel full; conv stem on {T_s}/3000 frames (x{3000 // T_s}); 1 of {L} layers with attention on all "
-            f"1500 positions ({threads} thread(s) over heads) and the scalar FFN on {R}/1500 rows, extrapolated by op count "
-            f"(mel {t_mel:.2f}s, stem {t_stem:.1f}s, layer {t_layer:.1f}s)")
+    desc = (f"1 chunk of {cfg_name}: mel {t_mel:.2f}s, whole conv stem (3000 frames) {t_stem:.1f}s, ONE complete encoder layer (1500 positions: "
+            f"attention with {threads} thread(s) over heads, scalar FFN on all 1500 rows) {t_layer:.1f}s, ln_post {t_ln:.3f}s -- all measured; "
+            f"chunk = mel + stem + {L} x layer + ln_post = {t_chunk:.0f}s")
     return CHUNK_SECONDS / t_chunk, desc, time.perf_counter() - t_all
 
 
-def run_reference(args, rank: int):
+def make_config(args, world, extra=None):
+    """The same keys in both arms (the driver compares the two config dicts)."""
+    B = args.chunks
+    cfg = {"workload": workload_name(args), "chunks_per_gpu_per_step": B, "global_chunks_per_step": world * B,
+           "apr_payload": args.quant, "out_dtype": args.out_dtype,
+           "l2": f"inputs rotate over 3 distinct batches ({3 * B * 1.92:.0f} MB) and each step streams ~2 GB of activations, both > 126 MB L2",
+           "parallelism": f"dp{world} (chunks sharded by batch, replicated weights, no data-path collective)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     from oracle import cref
     threads = cref.max_threads()
     cref.lib()
-    vals, spent, desc = [], [], ""
+    vals, desc, spent = [], "", 0.0
+    budget_s = 200.0                                  # the whole run ends within a few minutes whatever --steps says
     for i in range(args.warmup + args.steps):
-        v, desc, s = cpu_sample(args.model, threads)
-        if i >= args.warmup:
-            vals.append(v); spent.append(s)
-        if sum(spent) > 240:
+        v, desc, sec = cpu_sample(args.model, threads)
+        spent += sec
+        if i >= min(args.warmup, 1) or spent > budget_s:      # at most one untimed warm-up sample on the CPU
+            vals.append(v)
+        if spent > budget_s or len(vals) >= args.steps:
             break
     val = float(np.mean(vals))
     chunks = args.chunks
-    out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+    out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1),
            "ms_per_step": 1e3 * chunks * CHUNK_SECONDS / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "impl": "reference",
-           "config": {"workload": workload_name(args), "chunks_per_gpu_per_step": chunks,
-                      "note": "reference = the reference's own CPU algorithm (C restatement oracle/whisper_ref.c; the Rust crate cannot be "
-                              "built offline), one process on the host cores; throughput does not grow with --gpus"},
+           "config": make_config(args, world),
+           "note": "reference = the reference's own CPU algorithm (C restatement oracle/whisper_ref.c; the Rust crate cannot be built offline), "
+                   "one process on the host cores; a step here is one measured chunk sample, ms_per_step is scaled to the arm's chunks per step; "
+                   "throughput does not grow with --gpus",
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -166,6 +184,62 @@ def workload_name(args):
     return {"large-v3": "whisper-large-v3 shape (128 mel, 32 enc layers, d=1280) bf16, 30 s chunks sharded by batch",
             }.get(args.model, f"whisper-{args.model} shape bf16, 30 s chunks sharded by batch")
 
+
+
+def bench_gather(args, model, lib, dist, torch, rank, local_rank, world, B, S, d, dev_audio, ROT, timed, step_dev):
+    """`value_with_gather`: the same timed step with d_out = the gather rank's buffer (+ this rank's chunk offset)."""
+    import whisper_apr_b200
+    chk = whisper_apr_b200._lib.check
+    per_rank = B * S * d * 2
+    info = {"to_rank": 0, "dtype": "bf16", "bytes_per_rank": per_rank}
+    try:
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        base = C.c_void_p()
+        if rank == 0:
+            hb = (C.c_uint8 * 64)()
+            chk(lib.wb_ipc_alloc(local_rank, world * per_rank, C.byref(base), hb))
+            handle.copy_(torch.tensor(list(hb), dtype=torch.uint8))
+        dist.broadcast(handle, 0)
+        if rank != 0:
+            hb = (C.c_uint8 * 64)(*handle.cpu().tolist())
+            chk(lib.wb_ipc_open(local_rank, hb, C.byref(base)))
+        mine = base.value + rank * per_rank
+
+        def step_gather(i):
+            model.mel_encode_batch_dev(dev_audio[i % ROT].data_ptr(), B, mine, "bf16")
+
+        for i in range(2 * ROT):                   # every (input, destination) key twice: graphs captured before the timed region
+            step_gather(i)
+        torch.cuda.synchronize()
+        ms_g = timed(step_gather, args.steps)
+        # verification: what sits in rank 0's buffer at this rank's offset is what this rank computes locally for the same input
+        last = (args.steps - 1) % ROT
+        local = torch.empty((B, S, d), dtype=torch.bfloat16, device="cuda")
+        model.mel_encode_batch_dev(dev_audio[last].data_ptr(), B, local.data_ptr(), "bf16")
+        torch.cuda.synchronize()
+        got = np.empty(B * S * d, np.uint16)
+        chk(lib.wb_read_device(local_rank, C.c_void_p(mine), got.ctypes.data_as(C.c_void_p), got.nbytes))
+        same = bool(np.array_equal(got, local.view(torch.int16).cpu().numpy().view(np.uint16).ravel()))
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        info.update({"how": "peer stores over NVLink by the final LayerNorm kernel into rank 0's buffer (CUDA IPC mapping), inside the step",
+                     "ms_per_step": ms_g / args.steps, "value_with_gather": world * B * CHUNK_SECONDS * args.steps / (ms_g / 1e3),
+                     "verified_bit_identical": bool(flag.item())})
+        dist.barrier()
+        if rank != 0:
+            lib.wb_ipc_close(local_rank, base)
+        else:
+            torch.cuda.synchronize()
+            lib.wb_ipc_free(local_rank, base)
+    except Exception as e:                          # IPC unavailable in this container: NCCL all-gather of bf16 states, reported as such
+        from whisper_apr_b200 import sharding
+        out16 = torch.empty((B, S, d), dtype=torch.bfloat16, device="cuda")
+        for _ in range(2):
+            sharding.gather_states(out16, B * world)
+        ms_g = timed(lambda i: sharding.gather_states(out16, B * world), 5)
+        info.update({"how": f"fallback: nccl all_gather_into_tensor of bf16 states after the step (peer-store path failed: {e})",
+                     "ms_per_step_gather_only": ms_g / 5})
+    return info
 
 # ----------------------------------------------------------------------------------------------- our arm
 def main():
@@ -185,7 +259,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     if args.warmup < 3:
         args.warmup = 3                      # timing rule: >= 3 warm-up steps
@@ -204,7 +278,10 @@ def main():
     quant = {"f32": 0, "int8": 2, "int4": 3}[args.quant]
     t0 = time.time()
     data, _ = synth.random_model_apr(cfg, quant=quant, seed=0)
+    t1 = time.time()
     model = WhisperApr.load_from_apr(data, device=local_rank)
+    load_s = time.time() - t1                # wb_model_from_apr alone: .apr bytes in host memory -> weights resident in HBM
+    apr_mb = len(data) / 1e6
     del data
     model.set_max_batch(B)
     stream = torch.cuda.Stream()             # a real (non-legacy) stream: the kernels, copies and timing events all go here
@@ -294,15 +371,11 @@ def main():
         e2e = {"value": world * B * CHUNK_SECONDS * args.steps / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": B * synth.N_SAMPLES_30S * 4, "d2h_bytes_per_step": B * S * d * esz, "ms_per_step": ms_e / args.steps}
 
-    # optional final NVLink gather of the step's encoder states: reported beside the step, never inside `value`
+    # final NVLink gather of the step's encoder states to rank 0, INSIDE the step: every rank's final LayerNorm stores its
+    # bf16 states straight into rank 0's buffer over NVLink (peer stores through a CUDA-IPC mapping; no NCCL call, no extra pass).
     gather = None
     if world > 1:
-        from whisper_apr_b200 import sharding
-        for _ in range(2):
-            sharding.gather_states(dev_out, B * world)
-        ms_g = timed(lambda i: sharding.gather_states(dev_out, B * world), 5)
-        gather = {"ms_per_step": ms_g / 5, "bytes_per_rank": dev_out.numel() * dev_out.element_size(), "collective": "nccl all_gather_into_tensor"}
-
+        gather = bench_gather(args, model, lib, dist, torch, rank, local_rank, world, B, S, d, dev_audio, ROT, timed, step_dev)
     # per-kernel timing (CUDA events on the launching stream) over two more steps of the same region
     peaks = load_peaks()
     model.profile_enable(True)
@@ -345,22 +418,37 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, desc, _ = cpu_sample(args.model, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+            from oracle import cref
+            threads = cref.max_threads()
+            v, desc, _ = cpu_sample(args.model, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
         except Exception as e:      # the CPU baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+
+    # parity of THIS configuration at its real depth, measured by tests/test_gpu_full_depth.py on a B200 and committed under profiles/
+    parity = None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "parity_depth.json")))
+        key = {"large-v3": "large-v3 32L bf16 B=32", "base": "base 6L bf16 B=64", "small": "small 12L int8", "medium": "medium 24L int4"}.get(args.model)
+        if key in rec:
+            fin = rec[key]["final"]
+            first = fin.get("pos0", fin)
+            parity = {"config": key, "max_abs": first["max_abs"], "cos": first["cos"], "gate": {"max_abs": 2e-2, "cos": 0.9999},
+                      "source": "tests/test_gpu_full_depth.py (GPU vs float32 oracle, full depth), profiles/parity_depth.json"}
+    except Exception:
+        pass
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                "data": "synthetic",
-               "config": {"workload": workload_name(args), "chunks_per_gpu_per_step": B, "global_chunks_per_step": world * B,
-                          "apr_payload": args.quant, "out_dtype": args.out_dtype,
-                          "l2": f"inputs rotate over {ROT} distinct batches ({ROT * B * 1.92:.0f} MB) and each step streams ~2 GB of activations, both > 126 MB L2",
-                          "parallelism": f"dp{world} (chunks sharded by batch, replicated weights, no data-path collective)",
-                          "setup_s": round(setup_s, 1)},
+               "config": make_config(args, world),
+               "setup": {"load_s": round(load_s, 2), "apr_mb": round(apr_mb), "synth_and_load_s": round(setup_s, 1),
+                         "note": "load_s = wb_model_from_apr alone (pinned in-place upload + on-device conversion)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
-               "cpu_baseline": cpu, "gather": gather}
+               "cpu_baseline": cpu, "gather": gather, "parity": parity}
+        if gather and "value_with_gather" in gather:
+            out["value_with_gather"] = gather["value_with_gather"]
         print(json.dumps(out), flush=True)
     model.close()
     if world > 1:
