@@ -473,18 +473,3 @@ def test_per_channel_int8_requantisation(mel0):
         model.requantize_int8_per_channel()                                     # already quantised
     model.close()
 
-
-@pytest.mark.parametrize("M_,N,K", [(300, 1152, 384), (777, 1280, 1280)])
-def test_gemm_fp16_weight_format(M_, N, K):
-    """The B operand of tcgen05.mma kind::f16 may be IEEE fp16 while A stays bf16 (separate format fields of the instruction
-    descriptor): same rate, 8x finer weight rounding.  Result against the exactly-rounded operands."""
-    import torch
-    rng = np.random.default_rng(M_ + N)
-    A = rng.standard_normal((M_, K)).astype(np.float32)
-    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
-    bias = rng.standard_normal(N).astype(np.float32)
-    out = np.empty((M_, N), np.float32)
-    _lib.check(_lib.lib().wb_debug_gemm(0, _p(A), _p(W), _p(bias), None, M_, N, K, 4 | 0x100, C.c_float(1.0), _p(out)))
-    W16 = torch.from_numpy(W).to(torch.float16).to(torch.float64).numpy()
-    ref = _bf16_round(A).astype(np.float64) @ W16.T + bias
-    assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max() / 4)

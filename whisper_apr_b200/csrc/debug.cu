@@ -33,12 +33,9 @@ int wb_debug_gemm(int device, const float* A, const float* W, const float* bias,
   cudaMemcpy(fa.p, A, na * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(fw.p, W, nw * 4, cudaMemcpyHostToDevice);
   if (bias) cudaMemcpy(fb.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice);
-  const int w_fp16 = (epilogue & 0x100) ? 1 : 0;            // test switch: W held as IEEE fp16 (B format of the MMA descriptor)
-  epilogue &= 0xff;
   launch_f32_to_bf16(fa.p, ba.p, na, nullptr);
-  launch_f32_to_w16(fw.p, bw.p, nw, w_fp16, nullptr);
+  launch_f32_to_bf16(fw.p, bw.p, nw, nullptr);
   GemmDesc g{};
-  g.w_fp16 = w_fp16;
   g.A = ba.p; g.a_row_stride = K; g.a_batch_stride = static_cast<long long>(M) * K; g.rows_per_batch = M; g.n_batch = 1;
   g.W = bw.p; g.N = N; g.K = K; g.epilogue = epilogue; g.alpha = alpha; g.col_scale = nullptr; g.bias = bias ? fb.p : nullptr;
   g.ldc = N; g.out_rows_per_batch = M; g.out_row_off = 0; g.pe = nullptr;

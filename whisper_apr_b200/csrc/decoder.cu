@@ -459,7 +459,7 @@ int load_decoder(Replica* m, const AprFile& f, Uploader& up) {
     if ((rc = launch_fill_f32(tmp.p, 2 * d * d, 0.f, st)) != WB_OK) return rc;
     if ((rc = up.load_f32(p + ".encoder_attn.k_proj.weight", tmp.p, d * d)) || (rc = up.load_f32(p + ".encoder_attn.v_proj.weight", tmp.p + d * d, d * d))) return rc;
     if ((rc = dev_alloc(m, 2 * d * d, &lw.ca_wkv)) != WB_OK) return rc;
-    if ((rc = launch_f32_to_w16(tmp.p, lw.ca_wkv, 2 * d * d, m->w_fp16, st)) != WB_OK) return rc;
+    if ((rc = launch_f32_to_bf16(tmp.p, lw.ca_wkv, 2 * d * d, st)) != WB_OK) return rc;
     if ((rc = dev_alloc(m, 2 * d, &lw.ca_bkv)) || (rc = launch_fill_f32(lw.ca_bkv, 2 * d, 0.f, st))) return rc;
     if ((rc = up.load_f32(p + ".encoder_attn.k_proj.bias", lw.ca_bkv, d)) || (rc = up.load_f32(p + ".encoder_attn.v_proj.bias", lw.ca_bkv + d, d))) return rc;
     // FFN
@@ -500,7 +500,6 @@ static int cross_kv(Replica* m, const bf16* d_states, int B, int S) {
   const long long M = static_cast<long long>(B) * S;
   for (int l = 0; l < w.n_layers; ++l) {
     GemmDesc g{};
-    g.w_fp16 = m->w_fp16;
     g.A = d_states; g.a_row_stride = d; g.a_batch_stride = M * d; g.rows_per_batch = static_cast<int>(M); g.n_batch = 1;
     g.W = w.layers[l].ca_wkv; g.N = 2 * d; g.K = d;
     g.epilogue = EPI_BF16; g.alpha = 1.f; g.col_scale = nullptr; g.bias = w.layers[l].ca_bkv;

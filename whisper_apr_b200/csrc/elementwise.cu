@@ -1,7 +1,5 @@
 // HBM-bound helpers around the tensor-core kernels: LayerNorm, dtype expansion of `.apr` payloads,
 // conv-weight repacking and guard-row fills.
-#include <cuda_fp16.h>
-
 #include "ptx.cuh"
 #include "wb_internal.h"
 
@@ -154,22 +152,6 @@ __global__ void __launch_bounds__(256) i4_to_bf16_vec_kernel(const uint4* __rest
     }
   }
 }
-// fp16-target twins of the weight conversions (IEEE half bits written into the same 16-bit slots)
-__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2half_rn(in[i]);
-}
-__global__ void i8_to_f16_kernel(const int8_t* __restrict__ in, __half* __restrict__ out, size_t n) {
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2half_rn(static_cast<float>(in[i]));
-}
-__global__ void i4_to_f16_kernel(const uint8_t* __restrict__ in, __half* __restrict__ out, size_t n) {
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2half_rn(static_cast<float>(unpack_i4(in[i >> 1], i)));
-}
 __global__ void i8_to_f32_kernel(const int8_t* __restrict__ in, float scale, float* __restrict__ out, size_t n) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -261,30 +243,6 @@ int launch_i4_to_bf16(const uint8_t* in, __nv_bfloat16* out, size_t n, cudaStrea
     return WB_OK;
   }
   i4_to_bf16_kernel<<<grid_for(n), 256, 0, s>>>(in, out, n);
-  count_launch();
-  WB_CUDA_OK(cudaGetLastError());
-  return WB_OK;
-}
-int launch_f32_to_w16(const float* in, __nv_bfloat16* out, size_t n, int fp16, cudaStream_t s) {
-  if (!fp16) return launch_f32_to_bf16(in, out, n, s);
-  if (n == 0) return WB_OK;
-  f32_to_f16_kernel<<<grid_for(n), 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n);
-  count_launch();
-  WB_CUDA_OK(cudaGetLastError());
-  return WB_OK;
-}
-int launch_i8_to_w16(const int8_t* in, __nv_bfloat16* out, size_t n, int fp16, cudaStream_t s) {
-  if (!fp16) return launch_i8_to_bf16(in, out, n, s);
-  if (n == 0) return WB_OK;
-  i8_to_f16_kernel<<<grid_for(n), 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n);
-  count_launch();
-  WB_CUDA_OK(cudaGetLastError());
-  return WB_OK;
-}
-int launch_i4_to_w16(const uint8_t* in, __nv_bfloat16* out, size_t n, int fp16, cudaStream_t s) {
-  if (!fp16) return launch_i4_to_bf16(in, out, n, s);
-  if (n == 0) return WB_OK;
-  i4_to_f16_kernel<<<grid_for(n), 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;

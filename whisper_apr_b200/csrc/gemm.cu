@@ -44,7 +44,7 @@ struct GemmKParams {
   const float* bias;
   void* out;
   const float* pe;
-  uint32_t idesc;               // tcgen05 instruction descriptor (A bf16; B bf16 or fp16)
+  uint32_t idesc;               // tcgen05 instruction descriptor
 };
 
 // GELU (tanh form, encoder.rs:314-318) for bf16 outputs: one MUFU (tanh.approx.f32, relative error 2^-11) instead of the two
@@ -488,7 +488,6 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.out = g.out;
   kp.pe = g.pe;
   kp.idesc = umma_idesc_bf16(2 * BM, BN, 0);
-  if (g.w_fp16) kp.idesc &= ~(7u << 10);                  // B format field [10,13): 1 = bf16 -> 0 = fp16
   const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
   CUtensorMap tc = ta;                                    // the f32 debug / positional-embedding epilogues do not read it
   if (g.epilogue == EPI_BF16 || g.epilogue == EPI_GELU_BF16) {

@@ -7,8 +7,6 @@
 // stream (the caller's buffer is page-locked by wb_model_from_apr_devices for the duration, so the pieces are true DMA and the
 // call does not block); every tensor is then cut out of the image by a conversion kernel on the compute stream that waits only for
 // the piece holding its last byte.  No per-tensor synchronisation, no host-side staging vectors; the image is freed after the load.
-#include <cuda_fp16.h>
-
 #include "loader.h"
 
 namespace wb {
@@ -35,14 +33,13 @@ __global__ void copy_f32_unaligned_kernel(const uint8_t* __restrict__ src, float
     }
   }
 }
-__global__ void f32_unaligned_to_w16_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n, int fp16) {
+__global__ void f32_unaligned_to_bf16_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) {
     const uint8_t* p = src + 4 * i;
     const uint32_t u = p[0] | (p[1] << 8) | (p[2] << 16) | (static_cast<uint32_t>(p[3]) << 24);
-    if (fp16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(__uint_as_float(u));
-    else dst[i] = __float2bfloat16_rn(__uint_as_float(u));
+    dst[i] = __float2bfloat16_rn(__uint_as_float(u));
   }
 }
 // per-channel symmetric int8 of a bf16 weight matrix [rows][cols] (quantize_f32_to_i8_per_channel, model/quantized.rs:1769-1794 over
@@ -80,10 +77,10 @@ int launch_copy_f32_bytes(const uint8_t* src, float* dst, size_t n, cudaStream_t
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
-int launch_f32_bytes_to_w16(const uint8_t* src, bf16* dst, size_t n, int fp16, cudaStream_t s) {
+int launch_f32_bytes_to_bf16(const uint8_t* src, bf16* dst, size_t n, cudaStream_t s) {
   if (n == 0) return WB_OK;
-  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) return launch_f32_to_w16(reinterpret_cast<const float*>(src), dst, n, fp16, s);
-  f32_unaligned_to_w16_kernel<<<grid_for(n), 256, 0, s>>>(src, dst, n, fp16);
+  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) return launch_f32_to_bf16(reinterpret_cast<const float*>(src), dst, n, s);
+  f32_unaligned_to_bf16_kernel<<<grid_for(n), 256, 0, s>>>(src, dst, n);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
@@ -285,8 +282,6 @@ int load_replica(Replica* m, const AprFile& f, const uint8_t* /*pinned_base*/) {
   DeviceGuard guard(m->device);
   m->cfg = f.cfg;
   m->use_graphs = getenv("WB_NO_GRAPH") == nullptr;       // A/B switch: plain launches instead of graph replay
-  const char* wf = getenv("WB_WEIGHTS_FP16");
-  m->w_fp16 = (wf && wf[0] == '1') ? 1 : 0;
   if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) return set_error(WB_ERR_CUDA, "cudaStreamCreate failed");
   m->stream = m->own_stream;
   WB_CUDA_OK(cudaEventCreateWithFlags(&m->done_event, cudaEventDisableTiming));
@@ -313,7 +308,6 @@ int load_replica(Replica* m, const AprFile& f, const uint8_t* /*pinned_base*/) {
 // the per-row scale is applied per output column in the GEMM epilogue.
 int requantize_int8_per_channel(Replica* m) {
   if (m->quant != 0) return set_error(WB_ERR_MODEL, "per-channel requantisation needs a model loaded from f32 payloads");
-  if (m->w_fp16) return set_error(WB_ERR_MODEL, "per-channel requantisation reads bf16 weights (unset WB_WEIGHTS_FP16)");
   DeviceGuard guard(m->device);
   const size_t d = m->cfg.n_audio_state;
   int rc;

@@ -8,7 +8,7 @@ constexpr size_t PIECE = 64ull << 20;     // H2D granularity of the file image
 
 int launch_fill_f32(float* dst, size_t n, float v, cudaStream_t s);
 int launch_copy_f32_bytes(const uint8_t* src, float* dst, size_t n, cudaStream_t s);          // little-endian f32 bytes, any alignment
-int launch_f32_bytes_to_w16(const uint8_t* src, bf16* dst, size_t n, int fp16, cudaStream_t s);
+int launch_f32_bytes_to_bf16(const uint8_t* src, bf16* dst, size_t n, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------------------------
 struct Uploader {
@@ -116,9 +116,9 @@ struct Uploader {
     int rc = payload(name, count, &src, &n, &s);
     if (rc != WB_OK || n == 0) return rc;
     switch (f->cfg.quantization) {
-      case 2: *scale_out = s; return launch_i8_to_w16(reinterpret_cast<const int8_t*>(src), dst, n, m->w_fp16, m->stream);
-      case 3: *scale_out = s; return launch_i4_to_w16(src, dst, n, m->w_fp16, m->stream);
-      default: return launch_f32_bytes_to_w16(src, dst, n, m->w_fp16, m->stream);
+      case 2: *scale_out = s; return launch_i8_to_bf16(reinterpret_cast<const int8_t*>(src), dst, n, m->stream);
+      case 3: *scale_out = s; return launch_i4_to_bf16(src, dst, n, m->stream);
+      default: return launch_f32_bytes_to_bf16(src, dst, n, m->stream);
     }
   }
 };

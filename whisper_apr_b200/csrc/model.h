@@ -137,7 +137,6 @@ struct Replica {
   float conv1_s = 1.f, conv2_s = 1.f;
   float* pe = nullptr;
   std::vector<LayerW> layers;
-  int w_fp16 = 0;                       // GEMM weights held as IEEE fp16 instead of bf16 (WB_WEIGHTS_FP16=1 at load): see DESIGN.md, error budget
   int quant = 0;                        // 0: bf16 weights resident; 2 / 3: int8 / int4 payloads resident, expanded per layer
   bf16 *xp_qkv = nullptr, *xp_o = nullptr, *xp_1 = nullptr, *xp_2 = nullptr;   // expansion buffers (12 d^2 bf16: L2-sized)
   float *lnp_g = nullptr, *lnp_b = nullptr;

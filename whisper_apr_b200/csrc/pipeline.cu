@@ -60,7 +60,6 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.c1.p + static_cast<long long>(T + 1) * d, static_cast<long long>(T + 2) * d, B, d, st));
 
   GemmDesc g{};
-  g.w_fp16 = m->w_fp16;
   // conv1 + GELU: row t of the operand = padded frames t, t+1, t+2 (3*nm contiguous values)
   g.A = w.mel_bf16.p; g.a_row_stride = nm; g.a_batch_stride = static_cast<long long>(T + 2) * nm;
   g.rows_per_batch = T; g.n_batch = B;
@@ -79,7 +78,6 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   const int M = B * S;
   auto flat = [&](const bf16* A, int K, const bf16* W, int N, int epi, float alpha, const float* cs, const float* bias, void* out) {
     GemmDesc q{};
-    q.w_fp16 = m->w_fp16;
     q.A = A; q.a_row_stride = K; q.a_batch_stride = static_cast<long long>(M) * K; q.rows_per_batch = M; q.n_batch = 1;
     q.W = W; q.N = N; q.K = K; q.epilogue = epi; q.alpha = alpha; q.col_scale = cs; q.bias = bias;
     q.out = out; q.ldc = N; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
@@ -91,7 +89,7 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   // bf16 (39 MB for d = 1280) stay L2-resident for the GEMM that follows; HBM only ever holds the packed bytes.
   const size_t dd = static_cast<size_t>(d) * d;
   auto expand = [&](const uint8_t* packed, bf16* dst, size_t n) {
-    return m->quant == 2 ? launch_i8_to_w16(reinterpret_cast<const int8_t*>(packed), dst, n, m->w_fp16, st) : launch_i4_to_w16(packed, dst, n, m->w_fp16, st);
+    return m->quant == 2 ? launch_i8_to_bf16(reinterpret_cast<const int8_t*>(packed), dst, n, st) : launch_i4_to_bf16(packed, dst, n, st);
   };
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = m->layers[i];

@@ -75,7 +75,6 @@ struct GemmDesc {
   // W operand: bf16 [N][K] row-major (the reference's [out][in] layout, attention.rs:33-34)
   const __nv_bfloat16* W;
   int N, K;
-  int w_fp16 = 0;             // the W bits are IEEE fp16 (11-bit significand) instead of bf16: same MMA rate, B-format field of the descriptor
   // epilogue
   int epilogue;
   float alpha;
@@ -121,10 +120,6 @@ int mel_init();
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
                      float* out_f32, cudaStream_t stream);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
-// weight conversions with a selectable 16-bit target (fp16 != 0: IEEE half bits stored in the bf16-typed buffer)
-int launch_f32_to_w16(const float* in, __nv_bfloat16* out, size_t n, int fp16, cudaStream_t stream);
-int launch_i8_to_w16(const int8_t* in, __nv_bfloat16* out, size_t n, int fp16, cudaStream_t stream);
-int launch_i4_to_w16(const uint8_t* in, __nv_bfloat16* out, size_t n, int fp16, cudaStream_t stream);
 int launch_i8_to_bf16(const int8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
 int launch_i4_to_bf16(const uint8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
 int launch_i8_to_f32(const int8_t* in, float scale, float* out, size_t n, cudaStream_t stream);
