@@ -201,6 +201,71 @@ int wb_batch_preprocess(const wb_model* m, const float* const* audio, const size
 int wb_to_padded_tensor(const float* const* mels, const size_t* frame_counts, int B, size_t n_mels, size_t max_frames,
                         float* out);
 
+/* ---- ingest in front of the hot path: WAV, resampling, VAD ---------------------------- */
+/* What parse_wav (src/audio/wav.rs:99-224) finds in a RIFF/WAVE buffer.  sample_kind: 0 u8, 1 i16, 2 i24, 3 i32 PCM, 4 f32. */
+typedef struct wb_wav_info {
+  uint32_t sample_rate;
+  uint16_t channels, bits_per_sample, sample_kind, reserved;
+  uint64_t data_offset, data_bytes;
+  uint64_t n_frames; /* samples per channel == length of the mono result */
+} wb_wav_info;
+/* The chunk walk of parse_wav (fmt / WAVE_FORMAT_EXTENSIBLE / data; unknown chunks skipped with even alignment); host only, no GPU.
+ * Errors are WB_ERR_AUDIO with WavError's texts ("WAV file too small", "missing RIFF header", "missing WAVE format",
+ * "fmt chunk truncated", "unsupported format ..", "unsupported channel count ..", "no data chunk"). */
+int wb_wav_parse(const uint8_t* bytes, size_t n_bytes, wb_wav_info* out);
+/* parse_wav's payload half on the device: convert_{8,16,24,32}bit_pcm / convert_32bit_float + convert_to_mono (wav.rs:226-286):
+ * the raw payload is uploaded as it is, converted and down-mixed by one kernel.  out: info->n_frames mono f32 samples. */
+int wb_wav_decode(const wb_model* m, const uint8_t* bytes, size_t n_bytes, float* out, size_t out_capacity, wb_wav_info* info);
+/* SincResampler::resample (src/audio/resampler.rs:136-206; new / with_params :66-110): Kaiser-windowed sinc interpolation, f64
+ * accumulation, weight-normalised, output length ceil(n * target / source); same rates -> copy.  Errors as the reference:
+ * "sample rate must be non-zero", "kernel half-length must be non-zero", "cannot resample empty audio". */
+size_t wb_resample_len(size_t n, uint32_t source_rate, uint32_t target_rate);
+int wb_resample(const wb_model* m, const float* audio, size_t n, uint32_t source_rate, uint32_t target_rate, float* out,
+                size_t out_capacity, size_t* n_out);
+int wb_resample_with_params(const wb_model* m, const float* audio, size_t n, uint32_t source_rate, uint32_t target_rate,
+                            int kernel_half_len, double kaiser_beta, float* out, size_t out_capacity, size_t* n_out);
+/* WAV bytes -> mono -> 16 kHz with one upload of the raw payload and one download (what WhisperApr feeds compute_mel from a file). */
+int wb_ingest_wav_16k(const wb_model* m, const uint8_t* bytes, size_t n_bytes, float* out, size_t out_capacity, size_t* n_out,
+                      wb_wav_info* info);
+/* VadConfig (src/vad.rs:36-66). */
+typedef struct wb_vad_config {
+  uint32_t sample_rate, frame_size;
+  float energy_threshold, zcr_threshold;
+  uint32_t min_speech_frames, min_silence_frames;
+  float smoothing;
+} wb_vad_config;
+void wb_vad_config_default(wb_vad_config* c);
+/* VoiceActivityDetector::detect (src/vad.rs:554-607) for B streams at once: per-frame RMS energy and zero-crossing rate (one thread
+ * per frame, the reference's sequential f32 sums), then process_frame's state machine with its adaptive noise floor (one thread per
+ * stream, :609-672).  segments: [B][seg_capacity][3] = (start s, end s, mean energy); n_segments[B] (may exceed the capacity: the
+ * reference's count); frame_events (optional): per stream, one byte per frame, 0 Continue / 1 SpeechStart / 2 SpeechEnd;
+ * n_frames_out (optional) [B].  cfg == NULL: VadConfig::default(). */
+int wb_vad_detect_batch(const wb_model* m, const float* const* audio, const size_t* n_samples, int B, const wb_vad_config* cfg,
+                        float* segments, int seg_capacity, int* n_segments, uint8_t* const* frame_events, size_t* n_frames_out);
+
+/* ---- streaming front end on the device ------------------------------------------------- */
+/* audio::split_into_chunks (src/audio/batch.rs:219-240) + compute_mel + Encoder::forward_batch for every chunk of every stream without
+ * materialising the chunks: each stream is uploaded once and a chunk is an (offset, length) VIEW the mel kernel reads in place
+ * (samples past the view read as 0 = compute_mel's zero padding to 30 s, src/lib.rs:413-420).  out: [total chunks][1500][d],
+ * stream-major; chunk_counts [n_streams] and *total_chunks as split_into_chunks gives them.  Streams shard over the handle's devices. */
+int wb_stream_encode_views(const wb_model* m, const float* const* streams, const size_t* stream_lens, int n_streams, size_t chunk_size,
+                           size_t overlap, void* out, wb_dtype out_dtype, size_t out_capacity_chunks, size_t* chunk_counts,
+                           size_t* total_chunks);
+/* The chunk-assembly half of StreamingProcessor (src/audio/streaming.rs) for n_streams streams whose accumulators live in HBM:
+ * push = push_audio (:672-675); ready = has_chunk; encode = get_chunk (:843-870: [carried overlap | samples] zero padded to the chunk
+ * size, the chunk's last overlap_samples kept as the next chunk's prefix) -- or flush (:872-905) for every stream holding fresh audio --
+ * assembled by one kernel, then compute_mel + encoder over the assembled batch.  VAD gating is not part of the set: drive it with
+ * wb_vad_detect_batch and push what should be transcribed. */
+typedef struct wb_stream_set wb_stream_set;
+int wb_stream_set_new(const wb_model* m, int n_streams, size_t chunk_samples, size_t overlap_samples, wb_stream_set** out);
+void wb_stream_set_free(wb_stream_set* s);
+int wb_stream_set_push(wb_stream_set* s, const int* stream_ids, const float* const* samples, const size_t* n_samples, int count);
+int wb_stream_set_ready(const wb_stream_set* s, int* ids_out, int capacity);
+int wb_stream_set_encode(wb_stream_set* s, int flush, void* out, wb_dtype out_dtype, int* ids_out, size_t* n_valid_out, int capacity,
+                         int* n_chunks_out);
+/* test hook: the chunk batch the last wb_stream_set_encode assembled, [n][chunk_samples] f32 */
+int wb_debug_stream_set_chunks(const wb_stream_set* s, int n, float* out);
+
 /* ---- test hooks (not part of the reference surface) ------------------------------- */
 /* Host restatement of the kernel's FFT factorisation: P[201] = |rfft400(y)|^2.  No GPU needed. */
 void wb_debug_fft400_power_host(const float* y400, float* p201);

@@ -79,6 +79,34 @@ SIGNATURES = {
     "wb_debug_layernorm": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
 }
 
+class WbWavInfo(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint16), ("bits_per_sample", C.c_uint16), ("sample_kind", C.c_uint16),
+                ("reserved", C.c_uint16), ("data_offset", C.c_uint64), ("data_bytes", C.c_uint64), ("n_frames", C.c_uint64)]
+
+
+class WbVadConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("frame_size", C.c_uint32), ("energy_threshold", C.c_float), ("zcr_threshold", C.c_float),
+                ("min_speech_frames", C.c_uint32), ("min_silence_frames", C.c_uint32), ("smoothing", C.c_float)]
+
+
+SIGNATURES.update({
+    "wb_wav_parse": (C.c_int, [_vp, C.c_size_t, C.POINTER(WbWavInfo)]),
+    "wb_wav_decode": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(WbWavInfo)]),
+    "wb_resample_len": (C.c_size_t, [C.c_size_t, C.c_uint32, C.c_uint32]),
+    "wb_resample": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.c_uint32, _vp, C.c_size_t, _szp]),
+    "wb_resample_with_params": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_double, _vp, C.c_size_t, _szp]),
+    "wb_ingest_wav_16k": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp, C.POINTER(WbWavInfo)]),
+    "wb_vad_config_default": (None, [C.POINTER(WbVadConfig)]),
+    "wb_vad_detect_batch": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, C.POINTER(WbVadConfig), _vp, C.c_int, _vp, C.POINTER(_vp), _szp]),
+    "wb_stream_encode_views": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, C.c_size_t, C.c_size_t, _vp, C.c_int, C.c_size_t, _szp, _szp]),
+    "wb_stream_set_new": (C.c_int, [_vp, C.c_int, C.c_size_t, C.c_size_t, C.POINTER(_vp)]),
+    "wb_stream_set_free": (None, [_vp]),
+    "wb_stream_set_push": (C.c_int, [_vp, _vp, C.POINTER(_vp), _szp, C.c_int]),
+    "wb_stream_set_ready": (C.c_int, [_vp, _vp, C.c_int]),
+    "wb_stream_set_encode": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _szp, C.c_int, _vp]),
+    "wb_debug_stream_set_chunks": (C.c_int, [_vp, C.c_int, _vp]),
+})
+
 _lib = None
 
 

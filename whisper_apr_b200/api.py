@@ -425,3 +425,163 @@ def to_padded_tensor(mels, n_mels: int) -> np.ndarray:
 def bf16_bits_to_f32(a: np.ndarray) -> np.ndarray:
     """View raw bf16 bit patterns (uint16) as float32 values."""
     return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Ingest in front of the hot path (SURVEY 8f-3 / 8f-4): WAV, resampling, VAD, chunk views, streaming chunk assembly.
+@dataclass
+class WavData:
+    """audio::wav::WavData (src/audio/wav.rs:60-72)."""
+    samples: np.ndarray
+    sample_rate: int
+    original_channels: int
+    bits_per_sample: int
+
+
+def parse_wav_header(data: bytes) -> "_lib.WbWavInfo":
+    """The chunk walk of parse_wav (host only): format, channel count, payload location."""
+    buf = np.frombuffer(data, np.uint8)
+    info = _lib.WbWavInfo()
+    check(_lib.lib().wb_wav_parse(C.c_void_p(buf.ctypes.data if buf.size else 0), buf.size, C.byref(info)))
+    return info
+
+
+def parse_wav(model: WhisperApr, data: bytes) -> WavData:
+    """audio::wav::parse_wav (src/audio/wav.rs:99-224): samples converted and down-mixed on the model's device."""
+    buf = np.frombuffer(data, np.uint8)
+    info = parse_wav_header(data)
+    out = np.empty(int(info.n_frames), np.float32)
+    check(_lib.lib().wb_wav_decode(model._h, C.c_void_p(buf.ctypes.data), buf.size, _ptr(out), out.size, C.byref(info)))
+    return WavData(out, int(info.sample_rate), int(info.channels), int(info.bits_per_sample))
+
+
+class SincResampler:
+    """audio::SincResampler (src/audio/resampler.rs:28-250), resample() on the model's device."""
+
+    def __init__(self, model: WhisperApr, source_rate: int, target_rate: int, kernel_half_len: int = 16, kaiser_beta: float = 6.0):
+        if source_rate == 0 or target_rate == 0:
+            raise WhisperError(_lib.WB_ERR_AUDIO, "sample rate must be non-zero")
+        if kernel_half_len == 0:
+            raise WhisperError(_lib.WB_ERR_AUDIO, "kernel half-length must be non-zero")
+        self._m, self.source_rate, self.target_rate = model, source_rate, target_rate
+        self.kernel_half_len, self.kaiser_beta = kernel_half_len, kaiser_beta
+
+    @property
+    def ratio(self) -> float:
+        return float(self.target_rate) / float(self.source_rate)
+
+    def resample(self, audio) -> np.ndarray:
+        a = _f32(audio).ravel()
+        n_out = _lib.lib().wb_resample_len(a.size, self.source_rate, self.target_rate)
+        out = np.empty(max(int(n_out), 1), np.float32)
+        got = C.c_size_t(0)
+        check(_lib.lib().wb_resample_with_params(self._m._h, _ptr(a) if a.size else None, a.size, self.source_rate, self.target_rate,
+                                                  self.kernel_half_len, self.kaiser_beta, _ptr(out), out.size, C.byref(got)))
+        return out[: got.value]
+
+
+def ingest_wav_16k(model: WhisperApr, data: bytes):
+    """WAV bytes -> mono f32 at 16 kHz, conversion and resampling on the device -> (samples, WavData-like header info)."""
+    buf = np.frombuffer(data, np.uint8)
+    info = parse_wav_header(data)
+    n_out = _lib.lib().wb_resample_len(int(info.n_frames), int(info.sample_rate), 16000) if info.sample_rate else 0
+    out = np.empty(max(int(n_out), 1), np.float32)
+    got = C.c_size_t(0)
+    check(_lib.lib().wb_ingest_wav_16k(model._h, C.c_void_p(buf.ctypes.data), buf.size, _ptr(out), out.size, C.byref(got), C.byref(info)))
+    return out[: got.value], info
+
+
+def vad_detect_batch(model: WhisperApr, audio_batch, config: dict | None = None, seg_capacity: int = 64):
+    """VoiceActivityDetector::detect (src/vad.rs:554-607) for a batch of streams -> (segments per stream [(start, end, energy)],
+    per-frame events per stream)."""
+    streams = [_f32(a).ravel() for a in audio_batch]
+    B = len(streams)
+    cfg = _lib.WbVadConfig()
+    _lib.lib().wb_vad_config_default(C.byref(cfg))
+    for k, v in (config or {}).items():
+        setattr(cfg, k, v)
+    if B == 0:
+        return [], []
+    ptrs = (C.c_void_p * B)(*[s.ctypes.data for s in streams])
+    lens = (C.c_size_t * B)(*[s.size for s in streams])
+    segs = np.zeros((B, seg_capacity, 3), np.float32)
+    nseg = np.zeros(B, np.int32)
+    fs = int(cfg.frame_size)
+    events = [np.zeros(s.size // fs + 1, np.uint8) for s in streams]
+    eptrs = (C.c_void_p * B)(*[e.ctypes.data for e in events])
+    nfr = (C.c_size_t * B)()
+    check(_lib.lib().wb_vad_detect_batch(model._h, ptrs, lens, B, C.byref(cfg), _ptr(segs), seg_capacity, _ptr(nseg), eptrs, nfr))
+    out_segs = [[tuple(float(x) for x in segs[b, i]) for i in range(min(int(nseg[b]), seg_capacity))] for b in range(B)]
+    return out_segs, [events[b][: nfr[b]].tolist() for b in range(B)]
+
+
+def stream_encode_views(model: WhisperApr, streams, chunk_size: int, overlap: int, out_dtype: str = "f32"):
+    """split_into_chunks + compute_mel + encoder for every chunk of every stream, chunks read in place as views of the uploaded
+    streams -> (states [total][1500][d], chunk counts per stream)."""
+    ss = [_f32(s).ravel() for s in streams]
+    n = len(ss)
+    d = model.config.n_audio_state
+    S = (N_FRAMES_30S - 1) // 2 + 1
+    counts = (C.c_size_t * max(n, 1))()
+    total = C.c_size_t(0)
+    cap = sum(_lib.lib().wb_split_into_chunks(s.size, chunk_size, overlap, None, None, 0) for s in ss)
+    out = np.empty((cap, S, d), np.float32 if out_dtype == "f32" else np.uint16)
+    if n == 0:
+        return out, []
+    ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in ss])
+    lens = (C.c_size_t * n)(*[s.size for s in ss])
+    check(_lib.lib().wb_stream_encode_views(model._h, ptrs, lens, n, chunk_size, overlap, _ptr(out), WB_F32 if out_dtype == "f32" else WB_BF16,
+                                             cap, counts, C.byref(total)))
+    return out[: total.value], [int(counts[i]) for i in range(n)]
+
+
+class StreamSet:
+    """The chunk-assembly half of StreamingProcessor (src/audio/streaming.rs:672-675, 843-905) for many streams, accumulators in HBM."""
+
+    def __init__(self, model: WhisperApr, n_streams: int, chunk_samples: int, overlap_samples: int):
+        self._m, self.n_streams, self.chunk_samples, self.overlap_samples = model, n_streams, chunk_samples, overlap_samples
+        h = C.c_void_p()
+        check(_lib.lib().wb_stream_set_new(model._h, n_streams, chunk_samples, overlap_samples, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().wb_stream_set_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, stream_ids, samples):
+        arrs = [_f32(s).ravel() for s in samples]
+        n = len(arrs)
+        ids = np.ascontiguousarray(stream_ids, np.int32)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        lens = (C.c_size_t * max(n, 1))(*[a.size for a in arrs])
+        check(_lib.lib().wb_stream_set_push(self._h, _ptr(ids), ptrs, lens, n))
+
+    def ready(self) -> list:
+        ids = np.zeros(self.n_streams, np.int32)
+        n = _lib.lib().wb_stream_set_ready(self._h, _ptr(ids), ids.size)
+        return ids[:n].tolist()
+
+    def encode(self, flush: bool = False, out_dtype: str = "f32"):
+        """get_chunk (or flush) for every ready stream, assembled on the device, then mel + encoder ->
+        (states [n][1500][d], stream ids, valid samples per chunk)."""
+        d = self._m.config.n_audio_state
+        S = (N_FRAMES_30S - 1) // 2 + 1
+        cap = self.n_streams
+        out = np.empty((cap, S, d), np.float32 if out_dtype == "f32" else np.uint16)
+        ids = np.zeros(cap, np.int32)
+        valid = (C.c_size_t * cap)()
+        n = C.c_int(0)
+        check(_lib.lib().wb_stream_set_encode(self._h, int(flush), _ptr(out), WB_F32 if out_dtype == "f32" else WB_BF16, _ptr(ids), valid, cap, C.byref(n)))
+        return out[: n.value], ids[: n.value].tolist(), [int(valid[i]) for i in range(n.value)]
+
+    def debug_chunks(self, n: int) -> np.ndarray:
+        out = np.empty((n, self.chunk_samples), np.float32)
+        check(_lib.lib().wb_debug_stream_set_chunks(self._h, n, _ptr(out)))
+        return out

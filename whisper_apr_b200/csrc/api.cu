@@ -304,7 +304,7 @@ int wb_compute_mel_batch_dev(const wb_model* h, const float* d_audio, int B, flo
     const int nb = std::min(m->max_batch, B - b0);
     int rc = ensure_workspace(m, nb);
     if (rc != WB_OK) return rc;
-    rc = mel_device(m, d_audio + static_cast<size_t>(b0) * N_SAMPLES_30S, nullptr, nb, d_mel_out + static_cast<size_t>(b0) * per_out, false);
+    rc = mel_device(m, d_audio + static_cast<size_t>(b0) * N_SAMPLES_30S, N_SAMPLES_30S, nullptr, nullptr, nb, d_mel_out + static_cast<size_t>(b0) * per_out, false);
     if (rc != WB_OK) return rc;
   }
   return WB_OK;
@@ -385,7 +385,7 @@ int wb_mel_encode_batch_dev(const wb_model* h, const float* d_audio, int B, void
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = std::min(m->max_batch, B - b0);
     if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
-    if ((rc = mel_encode_step(m, d_audio + static_cast<size_t>(b0) * N_SAMPLES_30S, nullptr, nb,
+    if ((rc = mel_encode_step(m, d_audio + static_cast<size_t>(b0) * N_SAMPLES_30S, N_SAMPLES_30S, nullptr, nullptr, nb,
                               static_cast<uint8_t*>(d_out) + static_cast<size_t>(b0) * S * d * esz, out_dtype)) != WB_OK)
       return rc;
   }
@@ -527,7 +527,7 @@ int transcribe_shard(Replica* m, const float* const* audio, const size_t* n_samp
       if (n) WB_CUDA_OK(cudaMemcpyAsync(m->ws.audio.p + static_cast<size_t>(i) * N_SAMPLES_30S, audio[b0 + i], n * 4, cudaMemcpyHostToDevice, m->stream));
     }
     WB_CUDA_OK(cudaMemcpy(m->ws.n_valid.p, nv.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
-    if ((rc = mel_encode_step(m, m->ws.audio.p, m->ws.n_valid.p, nb, m->ws.out_bf16.p, WB_BF16)) != WB_OK) return rc;
+    if ((rc = mel_encode_step(m, m->ws.audio.p, N_SAMPLES_30S, nullptr, m->ws.n_valid.p, nb, m->ws.out_bf16.p, WB_BF16)) != WB_OK) return rc;
     if ((rc = decoder_greedy(m, m->ws.out_bf16.p, nb, init, n_init, max_tokens, suppress_ts, tokens_out + static_cast<size_t>(b0) * max_tokens,
                              lens_out + b0)) != WB_OK)
       return rc;

@@ -1,24 +1,31 @@
 // Fused log-mel front end: framing + periodic Hann + 400-point real FFT + |X|^2 + mel filterbank + log10,
 // with a per-chunk running maximum; then the Whisper clamp/scale and the frame-axis padding.
 //
-// Replaces MelFilterbank::compute (src/audio/mel.rs:233-310) and the padding rules of
-// WhisperApr::compute_mel (src/lib.rs:407-443).  Layout is frame-major [frame][mel] as the reference stores it
-// (mel.rs:298).  All arithmetic is fp32, as in the reference.
+// Replaces MelFilterbank::compute (src/audio/mel.rs:233-310), the padding rules of WhisperApr::compute_mel (src/lib.rs:407-443)
+// and -- in its ragged form -- BatchPreprocessor::process_batch's per-segment loop (src/audio/batch.rs:157-176).  Layout is
+// frame-major [frame][mel] as the reference stores it (mel.rs:298).  All arithmetic is fp32, as in the reference.
 //
-// Kernel 1 (mel_stft_kernel): one CTA per tile of 32 consecutive frames of one chunk.
-//   * the (31*hop + 400) samples the tile needs are staged in shared memory with coalesced 16-byte loads
-//     (each sample is read from HBM once per tile although it belongs to 2.5 frames),
-//   * the real frame is packed into a 200-point complex sequence; 200 = 8 x 25:
-//       step A  8 threads per frame, each a 25-point DFT (two layers of radix-5 butterflies) in registers,
-//               followed by the W200 twiddle, exchanged through shared memory;
-//       step B  13 tasks per frame, each two 8-point DFTs (columns k1 and 25-k1) whose outputs are exactly
-//               the conjugate-symmetric partners the real-FFT split needs, so the power spectrum is formed in
-//               registers and only P[0..200] goes back to shared memory,
-//   * the filterbank is applied over each mel row's non-zero span only (391 of 16080 weights for the slaney-80
-//     bank), k ascending like the reference's scalar loop; log10(max(.,1e-10)); coalesced store; block max
-//     -> one atomicMax per CTA on an order-preserving integer key.
-// Kernel 2 (mel_finalize_kernel): max(x, gmax-8), (x+4)/4, -1.0 for frames past the computed ones, written as f32
-//   [B][T][m] (API result) and/or bf16 [B][T+2][m] with zero guard rows (the conv1 GEMM's operand).
+// Kernel 1 (mel_stft_kernel), round-2 shape: a FRAME NEVER LEAVES ITS WARP.  A CTA of 8 warps owns a tile of 32 consecutive frames
+// of one segment; every warp owns 4 of them, 8 lanes per frame, and runs the whole chain on its own with __syncwarp only:
+//   load   lane (frame, n2) pulls its 25 sample pairs straight from global memory (coalesced 64 B runs per frame; the 2.5x overlap
+//          between neighbouring frames is served by L1) -- no CTA-wide staging buffer, no staging barrier;
+//   step A the real frame is packed into a 200-point complex sequence, 200 = 8 x 25: 25-point DFT (two layers of radix-5 butterflies)
+//          in registers, then the W200 twiddle, then ONE exchange through a warp-private 6.4 KB shared-memory slab (bank-conflict
+//          free for both access patterns at a frame stride of 200 complex values);
+//   step B 13 tasks per frame on its 8 lanes (two rounds): two 8-point DFTs (columns k1 and 25-k1) whose outputs are exactly the
+//          conjugate-symmetric partners the real-FFT split needs; the power spectrum is formed in registers and written back over
+//          the slab;
+//   mel    (frame, mel) pairs over the warp's lanes: filterbank over each row's non-zero span only (k ascending like the
+//          reference's scalar loop), log10(max(., 1e-10)), coalesced store, running max -> one atomicMax per warp on an
+//          order-preserving integer key.
+// The round-1 kernel staged all 32 frames' samples and all 32 z rows per CTA (93 KB) and crossed five __syncthreads per tile:
+// 16 resident warps per SM that all waited at the same barriers.  Here warps run out of phase with each other (one loads while
+// another does butterflies) and the slab is the only per-frame shared memory.
+// Segments are described by a MelBatch: fixed-size chunks at a stride, or -- through per-segment offset / length / row tables and
+// a tile table -- ragged segments and overlapping chunk VIEWS into longer streams (split_into_chunks without materialising chunks).
+// Kernel 2 (mel_finalize_kernel): max(x, gmax-8), (x+4)/4, -1.0 for frames past the computed ones, written as f32 [B][T][m]
+//   (API result) and/or bf16 [B][T+2][m] INCLUDING its two zero guard rows (the conv1 GEMM's operand); the block that finishes a
+//   chunk last re-arms the chunk's maximum for the next call, so a fused mel step is two launches.
 #include "fft400.cuh"
 #include "ptx.cuh"
 #include "wb_internal.h"
@@ -29,11 +36,11 @@ namespace {
 constexpr int NFFT = 400;
 constexpr int NFREQ = 201;
 constexpr int FT = 32;                 // frames per CTA
+constexpr int FW = 4;                  // frames per warp
 constexpr int MEL_THREADS = 256;
-constexpr int MAX_TILE = (FT - 1) * 160 + NFFT;          // 5360 samples for hop <= 160
-constexpr int SX_FLOATS = MAX_TILE + 16 * (FT + 3);      // + skew
-constexpr int ZSTRIDE = 200;           // complex per frame
-constexpr int PSTRIDE = 201;
+constexpr int ZS = 200;                // complex values per frame in the exchange slab (2*ZS % 32 == 16: see header)
+constexpr int PS = 216;                // floats per frame of the power spectrum inside the slab (PS % 32 == 24)
+constexpr int SLAB_FLOATS = FW * ZS * 2;       // 1600 floats = 6.4 KB per warp; the power rows (4 x 216) alias its front
 
 __constant__ float2 c_tw25[25];        // exp(-2*pi*i*b*c/25) at [b*5+c]
 
@@ -41,14 +48,10 @@ constexpr int FB_MAX = 2048;           // packed filterbank weights kept in shar
 constexpr int MEL_MAX = 256;
 
 struct MelSmem {
-  union {                              // the staged samples are dead once step A has run; the power spectrum takes their place
-    float x[SX_FLOATS];
-    float p[FT * PSTRIDE + 4];         // + 4: the zero-weighted padding of the last span may read up to 3 floats past bin 200
-  };
+  float slab[MEL_THREADS / 32][SLAB_FLOATS];
   float w[NFFT];
   float2 tw200[8 * 25];                // exp(-2*pi*i*n2*k1/200) at [n2*25+k1]
   float2 tw400[NFREQ + 1];             // exp(-2*pi*i*k/400)
-  float2 z[FT * ZSTRIDE];
   __align__(16) float fbw[FB_MAX];     // packed non-zero spans of the filterbank rows, each padded to a multiple of 4 weights
   int fb_lo[MEL_MAX], fb_len[MEL_MAX], fb_off[MEL_MAX];
 };
@@ -61,54 +64,49 @@ __device__ __forceinline__ float key_to_float(int k) {
   return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF);
 }
 
-template <int HOP>   // HOP == 160: skewed, conflict-free staging; HOP == 0: any hop, unskewed
-__device__ __forceinline__ int sx_index(int i, int hop) {
-  if (HOP == 160) return i + 16 * (i / 160);
-  return i;
-}
+struct MelKParams {
+  const float* audio;
+  long long audio_stride;
+  const long long* seg_off;
+  const int* n_valid;
+  int n_valid_all;
+  int hop;
+  int n_frames;
+  const int* n_frames_arr;
+  const long long* row_off;
+  const int2* tiles;
+  const float2* tw200_g;
+  const float2* tw400_g;
+  float* logmel;
+  int* max_key;
+};
 
-template <int HOP>
 __global__ void __launch_bounds__(MEL_THREADS, 2)
-mel_stft_kernel(const float* __restrict__ audio, long long audio_stride, const int* __restrict__ n_valid_arr, int n_valid_all,
-                int hop_rt, int n_frames, int frames_per_tile, MelTables tab, const float2* __restrict__ tw200_g,
-                const float2* __restrict__ tw400_g, float* __restrict__ logmel, int* __restrict__ chunk_max_key) {
+mel_stft_kernel(const MelKParams p, const MelTables tab) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   MelSmem& s = *reinterpret_cast<MelSmem*>(smem_raw);
-  const int hop = (HOP == 160) ? 160 : hop_rt;
-  const int tid = threadIdx.x;
-  const int b = blockIdx.y;
-  const int f0 = blockIdx.x * frames_per_tile;
-  const int nf = min(frames_per_tile, n_frames - f0);
-  const int n_valid = n_valid_arr ? n_valid_arr[b] : n_valid_all;
-  const float* chunk = audio + static_cast<long long>(b) * audio_stride;
-  const long long s0 = static_cast<long long>(f0) * hop;
-  const int tile_len = (nf - 1) * hop + NFFT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- stage samples, window, twiddles
-  if (HOP == 160) {
-    for (int i4 = tid; i4 < (tile_len >> 2); i4 += MEL_THREADS) {
-      const int i = i4 << 2;
-      const long long g = s0 + i;
-      float4 v;
-      if (g + 3 < n_valid) {
-        v = __ldg(reinterpret_cast<const float4*>(chunk + g));
-      } else {
-        v.x = g + 0 < n_valid ? chunk[g + 0] : 0.f;
-        v.y = g + 1 < n_valid ? chunk[g + 1] : 0.f;
-        v.z = g + 2 < n_valid ? chunk[g + 2] : 0.f;
-        v.w = g + 3 < n_valid ? chunk[g + 3] : 0.f;
-      }
-      *reinterpret_cast<float4*>(&s.x[sx_index<HOP>(i, hop)]) = v;    // 160 % 4 == 0: a float4 never straddles a skew step
-    }
+  // ---- which tile
+  int b, f0;
+  if (p.tiles) {
+    const int2 t = p.tiles[blockIdx.x];
+    b = t.x;
+    f0 = t.y;
   } else {
-    for (int i = tid; i < tile_len; i += MEL_THREADS) {
-      const long long g = s0 + i;
-      s.x[i] = g < n_valid ? chunk[g] : 0.f;
-    }
+    b = blockIdx.y;
+    f0 = blockIdx.x * FT;
   }
+  const int n_frames = p.n_frames_arr ? p.n_frames_arr[b] : p.n_frames;
+  const int n_valid = p.n_valid ? p.n_valid[b] : p.n_valid_all;
+  const float* seg = p.audio + (p.seg_off ? p.seg_off[b] : static_cast<long long>(b) * p.audio_stride);
+  const long long row0 = p.row_off ? p.row_off[b] : static_cast<long long>(b) * p.n_frames;
+  const int hop = p.hop;
+
+  // ---- tables (once per CTA)
   for (int i = tid; i < NFFT; i += MEL_THREADS) s.w[i] = tab.window[i];
-  for (int i = tid; i < 200; i += MEL_THREADS) s.tw200[i] = tw200_g[i];
-  for (int i = tid; i <= NFREQ; i += MEL_THREADS) s.tw400[i] = tw400_g[i];
+  for (int i = tid; i < 200; i += MEL_THREADS) s.tw200[i] = p.tw200_g[i];
+  for (int i = tid; i <= NFREQ; i += MEL_THREADS) s.tw400[i] = p.tw400_g[i];
   const bool fb_smem = tab.packed != nullptr;
   if (fb_smem) {
     for (int i = tid; i < tab.nnz; i += MEL_THREADS) s.fbw[i] = __ldg(tab.packed + i);
@@ -118,89 +116,138 @@ mel_stft_kernel(const float* __restrict__ audio, long long audio_stride, const i
       s.fb_off[i] = __ldg(tab.span_off + i);
     }
   }
-  __syncthreads();
+  __syncthreads();                     // the only CTA-wide barrier
 
-  // ---- step A: thread (f, n2): 25-point DFT over n1 of z[8*n1 + n2], then W200^(n2*k1)
+  const int fl = lane >> 3, n2 = lane & 7;
+  const int wf0 = f0 + warp * FW;                        // first frame of the warp
+  const int wnf = min(FW, n_frames - wf0);               // live frames of the warp
+  if (wnf <= 0) return;
+  const int f = wf0 + fl;                                // this lane group's frame
+  const bool live = fl < wnf;
+  float* slab = s.slab[warp];
+  float2* z = reinterpret_cast<float2*>(slab);
+
+  // ---- load + window + step A: 25-point DFT over n1 of z[8*n1 + n2], then W200^(n2*k1)
   {
-    const int f = tid >> 3, n2 = tid & 7;
-    if (f < nf) {
-      cf v[25];
-      const int base = f * hop + 2 * n2;
+    cf v[25];
+    const long long base = static_cast<long long>(f) * hop + 2 * n2;
+    const bool vec = (reinterpret_cast<uintptr_t>(seg + base) & 7) == 0;
 #pragma unroll
-      for (int n1 = 0; n1 < 25; ++n1) {
-        const int e = 16 * n1 + 2 * n2;            // sample index inside the frame (even)
-        const int i = base + 16 * n1;
-        float2 xs;
-        if (HOP == 160) {
-          xs = *reinterpret_cast<const float2*>(&s.x[sx_index<HOP>(i, hop)]);
+    for (int n1 = 0; n1 < 25; ++n1) {
+      const long long i = base + 16 * n1;
+      float2 xs = make_float2(0.f, 0.f);
+      if (live) {
+        if (vec && i + 1 < n_valid) {
+          xs = __ldg(reinterpret_cast<const float2*>(seg + i));
         } else {
-          xs.x = s.x[i];
-          xs.y = s.x[i + 1];
+          if (i < n_valid) xs.x = __ldg(seg + i);
+          if (i + 1 < n_valid) xs.y = __ldg(seg + i + 1);
         }
-        const float2 ws = *reinterpret_cast<const float2*>(&s.w[e]);
-        v[n1] = cmake(xs.x * ws.x, xs.y * ws.y);
       }
-      dft25(v, reinterpret_cast<const cf*>(c_tw25));
-      float2* zrow = &s.z[f * ZSTRIDE + n2 * 25];
+      const float2 ws = *reinterpret_cast<const float2*>(&s.w[16 * n1 + 2 * n2]);
+      v[n1] = cmake(xs.x * ws.x, xs.y * ws.y);
+    }
+    dft25(v, reinterpret_cast<const cf*>(c_tw25));
+    float2* zrow = z + fl * ZS + n2 * 25;
 #pragma unroll
-      for (int k1 = 0; k1 < 25; ++k1) {
-        const float2 t = s.tw200[n2 * 25 + k1];
-        const cf r = cmul(v[k1], cmake(t.x, t.y));
-        zrow[k1] = make_float2(r.x, r.y);
-      }
+    for (int k1 = 0; k1 < 25; ++k1) {
+      const float2 t = s.tw200[n2 * 25 + k1];
+      const cf r = cmul(v[k1], cmake(t.x, t.y));
+      zrow[k1] = make_float2(r.x, r.y);
     }
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- step B: task (f, p): 8-point DFTs of columns p and 25-p -> power spectrum in registers
-  for (int task = tid; task < nf * 13; task += MEL_THREADS) {
-    const int f = task / 13, pcol = task - f * 13;
-    const float2* zf = &s.z[f * ZSTRIDE];
-    float* pf = &s.p[f * PSTRIDE];
-    cf a[8];
+  // ---- step B: 13 tasks per frame on its 8 lanes, two rounds; the powers stay in registers until every z read is done
+  float pw0[16], pw1[16];
+  {
+    const float2* zf = z + fl * ZS;
+    {  // round 0: columns 0..7
+      const int pcol = n2;
+      cf a[8];
 #pragma unroll
-    for (int n2 = 0; n2 < 8; ++n2) { const float2 t = zf[n2 * 25 + pcol]; a[n2] = cmake(t.x, t.y); }
-    dft8(a);
-    if (pcol == 0) {
-      const float re0 = a[0].x + a[0].y, re200 = a[0].x - a[0].y;
-      pf[0] = re0 * re0;
-      pf[200] = re200 * re200;
+      for (int q = 0; q < 8; ++q) { const float2 t = zf[q * 25 + pcol]; a[q] = cmake(t.x, t.y); }
+      dft8(a);
+      if (pcol == 0) {
+        const float re0 = a[0].x + a[0].y, re200 = a[0].x - a[0].y;
+        pw0[0] = re0 * re0;
+        pw0[8] = re200 * re200;
 #pragma unroll
-      for (int k2 = 1; k2 < 8; ++k2) {
-        const float2 w = s.tw400[25 * k2];
-        pf[25 * k2] = rfft_power(a[k2], a[8 - k2], cmake(w.x, w.y));
+        for (int k2 = 1; k2 < 8; ++k2) {
+          const float2 w = s.tw400[25 * k2];
+          pw0[k2] = rfft_power(a[k2], a[8 - k2], cmake(w.x, w.y));
+          pw0[8 + k2] = 0.f;
+        }
+      } else {
+        cf c[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const float2 t = zf[q * 25 + 25 - pcol]; c[q] = cmake(t.x, t.y); }
+        dft8(c);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          const float2 w1 = s.tw400[pcol + 25 * k2], w2 = s.tw400[25 - pcol + 25 * k2];
+          pw0[k2] = rfft_power(a[k2], c[7 - k2], cmake(w1.x, w1.y));
+          pw0[8 + k2] = rfft_power(c[k2], a[7 - k2], cmake(w2.x, w2.y));
+        }
       }
-    } else {
-      cf c[8];
+    }
+    if (n2 < 5) {  // round 1: columns 8..12 on lanes 0..4 of the frame
+      const int pcol = 8 + n2;
+      cf a[8], c[8];
 #pragma unroll
-      for (int n2 = 0; n2 < 8; ++n2) { const float2 t = zf[n2 * 25 + 25 - pcol]; c[n2] = cmake(t.x, t.y); }
+      for (int q = 0; q < 8; ++q) { const float2 t = zf[q * 25 + pcol]; a[q] = cmake(t.x, t.y); }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const float2 t = zf[q * 25 + 25 - pcol]; c[q] = cmake(t.x, t.y); }
+      dft8(a);
       dft8(c);
 #pragma unroll
       for (int k2 = 0; k2 < 8; ++k2) {
-        const int k = pcol + 25 * k2;
-        const int kk = 25 - pcol + 25 * k2;
-        const float2 w1 = s.tw400[k], w2 = s.tw400[kk];
-        pf[k] = rfft_power(a[k2], c[7 - k2], cmake(w1.x, w1.y));
-        pf[kk] = rfft_power(c[k2], a[7 - k2], cmake(w2.x, w2.y));
+        const float2 w1 = s.tw400[pcol + 25 * k2], w2 = s.tw400[25 - pcol + 25 * k2];
+        pw1[k2] = rfft_power(a[k2], c[7 - k2], cmake(w1.x, w1.y));
+        pw1[8 + k2] = rfft_power(c[k2], a[7 - k2], cmake(w2.x, w2.y));
       }
     }
   }
-  if (tid < 4) s.p[FT * PSTRIDE + tid] = 0.f;      // the zero-weighted padding of the last span reads up to 3 floats past bin 200 of the last frame
-  __syncthreads();
+  __syncwarp();                        // every lane has read what it needs from z: the power rows may overwrite the slab
+  {
+    float* pf = slab + fl * PS;
+    if (n2 == 0) {
+      pf[0] = pw0[0];
+      pf[200] = pw0[8];
+#pragma unroll
+      for (int k2 = 1; k2 < 8; ++k2) pf[25 * k2] = pw0[k2];
+    } else {
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        pf[n2 + 25 * k2] = pw0[k2];
+        pf[25 - n2 + 25 * k2] = pw0[8 + k2];
+      }
+    }
+    if (n2 < 5) {
+      const int pcol = 8 + n2;
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        pf[pcol + 25 * k2] = pw1[k2];
+        pf[25 - pcol + 25 * k2] = pw1[8 + k2];
+      }
+    }
+    if (n2 == 7) { pf[201] = 0.f; pf[202] = 0.f; pf[203] = 0.f; }     // the zero-weighted padding of the last span reads up to 3 floats past bin 200
+  }
+  __syncwarp();
 
-  // ---- filterbank over non-zero spans, log10, store, running max
+  // ---- filterbank over non-zero spans, log10, store, running max: (frame, mel) pairs of the warp's frames over its 32 lanes
   const int m = tab.n_mels;
   float lmax = -INFINITY;
-  float* out = logmel + (static_cast<long long>(b) * n_frames + f0) * m;
+  float* out = p.logmel + (row0 + wf0) * m;
   if (fb_smem) {
-    // (frame, mel) pairs walked without a division per item; weights and spans from shared memory; log10 = log2 * log10(2)
+    // pairs walked without a division per item; weights and spans from shared memory; log10 = log2 * log10(2)
     // (MUFU.LG2: absolute error ~1e-7 on values of order 1-10, three orders below the 1e-4 gate)
-    int f = tid / m, j = tid - f * m;
-    const int df = MEL_THREADS / m, dj = MEL_THREADS - df * m;
-    for (int idx = tid; idx < nf * m; idx += MEL_THREADS) {
+    int ff = lane / m, j = lane - ff * m;
+    const int df = 32 / m, dj = 32 - df * m;
+    for (int idx = lane; idx < wnf * m; idx += 32) {
       const int len = s.fb_len[j];
       const float* fr = &s.fbw[s.fb_off[j]];
-      const float* pf = &s.p[f * PSTRIDE + s.fb_lo[j]];
+      const float* pf = slab + ff * PS + s.fb_lo[j];
       float e = 0.f;
       for (int k = 0; k < len; k += 4) {                          // k ascending, f32 (mel.rs:290-295); padding weights are 0
         const float4 w4 = *reinterpret_cast<const float4*>(fr + k);
@@ -212,16 +259,16 @@ mel_stft_kernel(const float* __restrict__ audio, long long audio_stride, const i
       const float v = __log2f(fmaxf(e, 1e-10f)) * 0.30102999566398120f;
       out[idx] = v;
       lmax = fmaxf(lmax, v);
-      f += df;
+      ff += df;
       j += dj;
-      if (j >= m) { j -= m; ++f; }
+      if (j >= m) { j -= m; ++ff; }
     }
   } else {
-    for (int idx = tid; idx < nf * m; idx += MEL_THREADS) {
-      const int f = idx / m, j = idx - f * m;
+    for (int idx = lane; idx < wnf * m; idx += 32) {
+      const int ff = idx / m, j = idx - ff * m;
       const int lo = __ldg(tab.span_lo + j), len = __ldg(tab.span_len + j);
       const float* fr = tab.filters + j * NFREQ + lo;
-      const float* pf = &s.p[f * PSTRIDE + lo];
+      const float* pf = slab + ff * PS + lo;
       float e = 0.f;
       for (int k = 0; k < len; ++k) e += __ldg(fr + k) * pf[k];      // k ascending, f32 (mel.rs:290-295)
       const float v = log10f(fmaxf(e, 1e-10f));
@@ -231,7 +278,7 @@ mel_stft_kernel(const float* __restrict__ audio, long long audio_stride, const i
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  if ((tid & 31) == 0) atomicMax(chunk_max_key + b, max_key(lmax));      // one atomic per warp: no block barrier at the tail
+  if (lane == 0) atomicMax(p.max_key + b, max_key(lmax));          // one atomic per warp
 }
 
 __global__ void mel_init_max_kernel(int* keys, int B) {
@@ -239,47 +286,58 @@ __global__ void mel_init_max_kernel(int* keys, int B) {
   if (i < B) keys[i] = max_key(-INFINITY);
 }
 
-// one thread per 4 consecutive (frame, mel) values of the padded output
+// One thread per 4 consecutive values of the padded output INCLUDING the bf16 operand's two guard rows: row r of [0, T_out + 2)
+// is a zero guard row for r == 0 and r == T_out + 1, frame r - 1 otherwise.  The last block of a chunk re-arms its max key.
 __global__ void __launch_bounds__(256)
-mel_finalize_kernel(const float* __restrict__ logmel, const int* __restrict__ chunk_max_key, int n_frames, int T_out, int m,
-                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+mel_finalize_kernel(const float* __restrict__ logmel, int* __restrict__ chunk_max_key, int n_frames, int T_out, int m,
+                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, unsigned int* __restrict__ done_counter) {
   const int b = blockIdx.y;
-  const long long per_chunk = static_cast<long long>(T_out) * m;
+  const long long per_padded = static_cast<long long>(T_out + 2) * m;
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i >= per_chunk) return;
   const float floor_v = key_to_float(chunk_max_key[b]) - 8.0f;
-  const long long n_real = static_cast<long long>(min(n_frames, T_out)) * m;
-  float v[4];
-  if (i + 3 < n_real) {
-    const float4 t = *reinterpret_cast<const float4*>(logmel + static_cast<long long>(b) * n_frames * m + i);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  if (i < per_padded) {
+    const long long r = i / m;                       // m % 4 == 0: the four values share a row
+    const bool guard = r == 0 || r == T_out + 1;
+    const long long fi = i - m;                      // index into the [T_out][m] frame block
+    const long long n_real = static_cast<long long>(min(n_frames, T_out)) * m;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!guard) {
+      if (fi < n_real) {                             // n_real is a multiple of m, hence of 4: the group is all real or all padding
+        const float4 t = *reinterpret_cast<const float4*>(logmel + static_cast<long long>(b) * n_frames * m + fi);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (fmaxf(v[k], floor_v) + 4.0f) / 4.0f;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (i + k < n_real) {
-        const float t = logmel[static_cast<long long>(b) * n_frames * m + i + k];
-        v[k] = (fmaxf(t, floor_v) + 4.0f) / 4.0f;
+        for (int k = 0; k < 4; ++k) v[k] = (fmaxf(v[k], floor_v) + 4.0f) / 4.0f;
       } else {
-        v[k] = -1.0f;                         // lib.rs:431-437 pad value
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = -1.0f;     // lib.rs:431-437 pad value
       }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + static_cast<long long>(b) * T_out * m + fi) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (out_bf16) {
+      uint2 w;
+      w.x = pack_bf16x2(v[0], v[1]);
+      w.y = pack_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(b) * per_padded + i) = w;
     }
   }
-  if (out_f32) *reinterpret_cast<float4*>(out_f32 + b * per_chunk + i) = make_float4(v[0], v[1], v[2], v[3]);
-  if (out_bf16) {
-    __nv_bfloat16* o = out_bf16 + static_cast<long long>(b) * (T_out + 2) * m + m + i;     // skip guard row 0
-    uint2 w;
-    w.x = pack_bf16x2(v[0], v[1]);
-    w.y = pack_bf16x2(v[2], v[3]);
-    *reinterpret_cast<uint2*>(o) = w;
+  // re-arm: the block that finishes last for this chunk resets the key (every block has read it above)
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(done_counter + b, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    chunk_max_key[b] = max_key(-INFINITY);
+    done_counter[b] = 0;
   }
 }
 
 // any n_mels: one value per thread
 __global__ void __launch_bounds__(256)
 mel_finalize_scalar_kernel(const float* __restrict__ logmel, const int* __restrict__ chunk_max_key, int n_frames, int T_out, int m,
-                           float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+                           float* __restrict__ out_f32) {
   const int b = blockIdx.y;
   const long long per_chunk = static_cast<long long>(T_out) * m;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -288,8 +346,19 @@ mel_finalize_scalar_kernel(const float* __restrict__ logmel, const int* __restri
   const long long n_real = static_cast<long long>(min(n_frames, T_out)) * m;
   float v = -1.0f;
   if (i < n_real) v = (fmaxf(logmel[static_cast<long long>(b) * n_frames * m + i], floor_v) + 4.0f) / 4.0f;
-  if (out_f32) out_f32[b * per_chunk + i] = v;
-  if (out_bf16) out_bf16[static_cast<long long>(b) * (T_out + 2) * m + m + i] = __float2bfloat16_rn(v);
+  out_f32[b * per_chunk + i] = v;
+}
+
+// ragged: segment b owns rows [row_off[b], row_off[b] + n_frames[b]); in place (out may alias logmel)
+__global__ void __launch_bounds__(256)
+mel_finalize_ragged_kernel(const float* logmel, const int* __restrict__ max_keys, const int* __restrict__ n_frames_arr,
+                           const long long* __restrict__ row_off, int m, float* out) {
+  const int b = blockIdx.y;
+  const long long n = static_cast<long long>(n_frames_arr[b]) * m;
+  const float floor_v = key_to_float(max_keys[b]) - 8.0f;
+  const long long base = row_off[b] * m;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[base + i] = (fmaxf(logmel[base + i], floor_v) + 4.0f) / 4.0f;
 }
 
 // twiddle tables live on ONE device; a process that drives several GPUs gets a set per device (PerDeviceOnce)
@@ -322,53 +391,71 @@ int mel_init() {
     WB_CUDA_OK(cudaMalloc(&g_tw400[dev], sizeof tw400));
     WB_CUDA_OK(cudaMemcpy(g_tw200[dev], tw200, sizeof tw200, cudaMemcpyHostToDevice));
     WB_CUDA_OK(cudaMemcpy(g_tw400[dev], tw400, sizeof tw400, cudaMemcpyHostToDevice));
-    WB_CUDA_OK(cudaFuncSetAttribute(mel_stft_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
-    WB_CUDA_OK(cudaFuncSetAttribute(mel_stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
+    WB_CUDA_OK(cudaFuncSetAttribute(mel_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
     return WB_OK;
   });
 }
 
-int launch_mel_stft(const float* audio, long long audio_stride, const int* n_valid, int padded_len, int hop, int n_frames, int B,
-                    const MelTables& t, float* logmel, int* chunk_max_key, cudaStream_t stream) {
-  int rc = mel_init();
-  if (rc != WB_OK) return rc;
-  if (B <= 0 || n_frames <= 0) return WB_OK;
-  const int dev = current_device();
-  mel_init_max_kernel<<<(B + 255) / 256, 256, 0, stream>>>(chunk_max_key, B);
-  count_launch();
-  int fpt = FT;
-  if (hop > 160) {
-    fpt = (MAX_TILE - NFFT) / hop + 1;
-    if (fpt < 1) fpt = 1;
-    if (fpt > FT) fpt = FT;
-  }
-  dim3 grid((n_frames + fpt - 1) / fpt, B);
-  const bool fast = hop == 160 && (audio_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(audio) & 15) == 0);
-  if (fast) {
-    mel_stft_kernel<160><<<grid, MEL_THREADS, sizeof(MelSmem), stream>>>(audio, audio_stride, n_valid, padded_len, hop, n_frames,
-                                                                         fpt, t, g_tw200[dev], g_tw400[dev], logmel, chunk_max_key);
-  } else {
-    mel_stft_kernel<0><<<grid, MEL_THREADS, sizeof(MelSmem), stream>>>(audio, audio_stride, n_valid, padded_len, hop, n_frames, fpt,
-                                                                       t, g_tw200[dev], g_tw400[dev], logmel, chunk_max_key);
-  }
+int launch_mel_init_keys(int* keys, int B, cudaStream_t stream) {
+  if (B <= 0) return WB_OK;
+  mel_init_max_kernel<<<(B + 255) / 256, 256, 0, stream>>>(keys, B);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
 
-int launch_mel_finalize(const float* logmel, const int* chunk_max_key, int n_frames, int T_out, int n_mels, int B, float* out_f32,
-                        __nv_bfloat16* out_bf16_padded, cudaStream_t stream) {
+int launch_mel_stft(const MelBatch& job, const MelTables& t, float* logmel, int* chunk_max_key, cudaStream_t stream) {
+  int rc = mel_init();
+  if (rc != WB_OK) return rc;
+  if (job.B <= 0) return WB_OK;
+  const int dev = current_device();
+  MelKParams p;
+  p.audio = job.audio; p.audio_stride = job.audio_stride; p.seg_off = job.seg_off; p.n_valid = job.n_valid; p.n_valid_all = job.n_valid_all;
+  p.hop = job.hop; p.n_frames = job.n_frames; p.n_frames_arr = job.n_frames_arr; p.row_off = job.row_off; p.tiles = job.tiles;
+  p.tw200_g = g_tw200[dev]; p.tw400_g = g_tw400[dev]; p.logmel = logmel; p.max_key = chunk_max_key;
+  dim3 grid;
+  if (job.tiles) {
+    if (job.n_tiles <= 0) return WB_OK;
+    grid = dim3(job.n_tiles, 1);
+  } else {
+    if (job.n_frames <= 0) return WB_OK;
+    grid = dim3((job.n_frames + FT - 1) / FT, job.B);
+  }
+  mel_stft_kernel<<<grid, MEL_THREADS, sizeof(MelSmem), stream>>>(p, t);
+  count_launch();
+  WB_CUDA_OK(cudaGetLastError());
+  return WB_OK;
+}
+
+int launch_mel_finalize(const float* logmel, int* chunk_max_key, unsigned int* done_counter, int n_frames, int T_out, int n_mels, int B,
+                        float* out_f32, __nv_bfloat16* out_bf16_padded, cudaStream_t stream) {
   if (B <= 0 || T_out <= 0) return WB_OK;
-  const long long per_chunk = static_cast<long long>(T_out) * n_mels;
   if (n_mels % 4 == 0) {
-    dim3 grid(static_cast<unsigned>((per_chunk / 4 + 255) / 256), B);
-    mel_finalize_kernel<<<grid, 256, 0, stream>>>(logmel, chunk_max_key, n_frames, T_out, n_mels, out_f32, out_bf16_padded);
+    const long long per_padded = static_cast<long long>(T_out + 2) * n_mels;
+    dim3 grid(static_cast<unsigned>((per_padded / 4 + 255) / 256), B);
+    mel_finalize_kernel<<<grid, 256, 0, stream>>>(logmel, chunk_max_key, n_frames, T_out, n_mels, out_f32, out_bf16_padded, done_counter);
     count_launch();
   } else {
+    if (out_bf16_padded || !out_f32) return set_error(WB_ERR_MODEL, "the bf16 conv operand needs n_mels % 4 == 0");
+    const long long per_chunk = static_cast<long long>(T_out) * n_mels;
     dim3 grid(static_cast<unsigned>((per_chunk + 255) / 256), B);
-    mel_finalize_scalar_kernel<<<grid, 256, 0, stream>>>(logmel, chunk_max_key, n_frames, T_out, n_mels, out_f32, out_bf16_padded);
+    mel_finalize_scalar_kernel<<<grid, 256, 0, stream>>>(logmel, chunk_max_key, n_frames, T_out, n_mels, out_f32);
     count_launch();
+    const int rc = launch_mel_init_keys(chunk_max_key, B, stream);     // re-arm for the next call
+    if (rc != WB_OK) return rc;
   }
+  WB_CUDA_OK(cudaGetLastError());
+  return WB_OK;
+}
+
+int launch_mel_finalize_ragged(const float* logmel, const int* max_keys, const int* n_frames_arr, const long long* row_off, int n_mels, int B,
+                               long long max_rows, float* out, cudaStream_t stream) {
+  if (B <= 0 || max_rows <= 0) return WB_OK;
+  long long g = (max_rows * n_mels + 255) / 256;
+  if (g > 1024) g = 1024;
+  dim3 grid(static_cast<unsigned>(g), B);
+  mel_finalize_ragged_kernel<<<grid, 256, 0, stream>>>(logmel, max_keys, n_frames_arr, row_off, n_mels, out);
+  count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }

@@ -116,7 +116,9 @@ struct Workspace {
   int cap = 0;
   DevBuf<float> audio, logmel, mel_f32, x, out_f32;
   DevBuf<int> n_valid, max_key;
+  DevBuf<unsigned int> mel_done;        // [B] zeroed: mel_finalize's last-block protocol
   DevBuf<bf16> mel_bf16, c1, xn, qkv, att, hid, out_bf16;
+  int guard_T = -1;                     // T for which c1's zero guard rows (conv2's padding) are in place
 };
 
 enum ProfCat { PC_MEL_STFT = 0, PC_MEL_FINALIZE = 1, PC_GEMM = 2, PC_ATTENTION = 3, PC_LAYERNORM = 4, PC_OTHER = 5, PC_COUNT = 6 };
@@ -142,6 +144,14 @@ struct Replica {
   float *lnp_g = nullptr, *lnp_b = nullptr;
   DecoderW dec;
   Workspace ws;
+  // ragged mel batches (BatchPreprocessor::process_batch, MelFilterbank::compute): arena, rows and host staging, reused
+  struct Ragged {
+    DevBuf<float> audio, logmel;
+    DevBuf<int> keys;
+    DevBuf<uint8_t> tables;
+    std::vector<uint8_t> h_tables;
+    std::vector<float> h_audio, h_out;
+  } rag;
   // copy/compute overlap of the host-buffer entry point: two staging slots, copy-in and copy-out streams
   struct Slot {
     DevBuf<float> audio;
@@ -157,7 +167,8 @@ struct Replica {
   // CUDA graphs of the fused mel + encoder step, keyed by its device pointers and batch size: the step is ~230 launches and as
   // many host-side tensor-map encodes; a replay is one cudaGraphLaunch.  First sighting of a key runs eagerly, the second is captured.
   struct StepGraph {
-    const void* in = nullptr; const void* n_valid = nullptr; void* out = nullptr; int B = 0; int dtype = 0;
+    const void* in = nullptr; const void* n_valid = nullptr; const void* seg_off = nullptr; long long stride = 0;
+    void* out = nullptr; int B = 0; int dtype = 0;
     int seen = 0; cudaGraphExec_t exec = nullptr; long long launches = 0;
   };
   std::vector<StepGraph> graphs;
@@ -226,10 +237,12 @@ int check_encoder_dims(const Replica* m);
 int check_fused_dims(const Replica* m);
 int validate_mel_len(const Replica* m, size_t mel_len, int* T_out);
 int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int n_layers, bool ln_post);
-int mel_device(Replica* m, const float* d_audio, const int* d_n_valid, int B, float* d_mel_f32, bool want_bf16);
+int mel_device(Replica* m, const float* d_audio, long long audio_stride, const long long* d_seg_off, const int* d_n_valid, int B,
+               float* d_mel_f32, bool want_bf16);
 int encode_same_len(Replica* m, const float* const* mels, const float* d_mel, int B, int T, void* out_host, void* out_dev,
                     size_t out_stride_elems, wb_dtype dt, int n_layers, bool ln_post);
-int mel_encode_step(Replica* m, const float* d_audio, const int* d_n_valid, int nb, void* d_out, wb_dtype out_dtype);
+int mel_encode_step(Replica* m, const float* d_audio, long long audio_stride, const long long* d_seg_off, const int* d_n_valid, int nb,
+                    void* d_out, wb_dtype out_dtype);
 // micro-batch `mb` of this replica's share: audio H2D on the copy-in stream, fused step, then either the D2H of the states on the
 // copy-out stream (out_host) or nothing more (states were written to d_out_final, possibly a peer device's memory, by ln_post)
 int enqueue_microbatch(Replica* m, const float* const* audio, const size_t* n_samples, int nb, void* out_host, void* d_out_final,

@@ -24,6 +24,9 @@ int ensure_workspace(Replica* m, int B) {
   if ((rc = w.audio.ensure(b * N_SAMPLES_30S)) != WB_OK) return rc;
   if ((rc = w.n_valid.ensure(b)) != WB_OK) return rc;
   if ((rc = w.max_key.ensure(b)) != WB_OK) return rc;
+  if ((rc = w.mel_done.ensure(b)) != WB_OK) return rc;
+  WB_CUDA_OK(cudaMemsetAsync(w.mel_done.p, 0, b * sizeof(unsigned int), m->stream));
+  if ((rc = launch_mel_init_keys(w.max_key.p, B, m->stream)) != WB_OK) return rc;    // armed once; mel_finalize re-arms after every use
   if ((rc = w.logmel.ensure(b * T * nm)) != WB_OK) return rc;
   if ((rc = w.mel_f32.ensure(b * T * nm)) != WB_OK) return rc;
   if ((rc = w.mel_bf16.ensure(b * (T + 2) * nm)) != WB_OK) return rc;
@@ -36,6 +39,7 @@ int ensure_workspace(Replica* m, int B) {
   if ((rc = w.out_f32.ensure(b * S * d)) != WB_OK) return rc;
   if ((rc = w.out_bf16.ensure(b * S * d)) != WB_OK) return rc;
   w.cap = B;
+  w.guard_T = -1;
   for (auto& g : m->graphs)                 // workspace pointers are baked into captured launches
     if (g.exec) cudaGraphExecDestroy(g.exec);
   m->graphs.clear();
@@ -55,9 +59,12 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   NvtxRange nvtx("step_g_encode");            // the reference's renacer span of the encoder stage (.renacer.toml:11-32)
   const int L = n_layers < 0 ? static_cast<int>(m->layers.size()) : std::min<int>(n_layers, static_cast<int>(m->layers.size()));
 
-  // c1 guard rows (0 and T+1) are zero: conv2's padding
-  WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.c1.p, static_cast<long long>(T + 2) * d, B, d, st));
-  WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.c1.p + static_cast<long long>(T + 1) * d, static_cast<long long>(T + 2) * d, B, d, st));
+  // c1 guard rows (0 and T+1 of every batch entry) are zero: conv2's padding.  conv1 only ever writes rows 1..T, so they stay zero
+  // from one step to the next; they are re-laid only when T (the row pitch of the batch entries) changes.
+  if (w.guard_T != T) {
+    WB_CUDA_OK(cudaMemsetAsync(w.c1.p, 0, w.c1.n * sizeof(bf16), st));
+    w.guard_T = T;
+  }
 
   GemmDesc g{};
   // conv1 + GELU: row t of the operand = padded frames t, t+1, t+2 (3*nm contiguous values)
@@ -120,20 +127,18 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
 
 // mel of B chunks already in ws.audio ([B][480000], n_valid per chunk in ws.n_valid) -> optional f32 [B][3000][m] and/or
 // the bf16 padded operand in ws.mel_bf16.
-int mel_device(Replica* m, const float* d_audio, const int* d_n_valid, int B, float* d_mel_f32, bool want_bf16) {
+int mel_device(Replica* m, const float* d_audio, long long audio_stride, const long long* d_seg_off, const int* d_n_valid, int B,
+               float* d_mel_f32, bool want_bf16) {
   Workspace& w = m->ws;
   const int nm = m->mel.n_mels;
   const int n_frames = (N_SAMPLES_30S - N_FFT) / HOP + 1;     // 2998 (mel.rs:245-249)
   int rc;
   NvtxRange nvtx("step_f_mel");               // the reference's span name for MelFilterbank::compute (src/audio/mel.rs:234)
-  WB_PROF(PC_MEL_STFT, launch_mel_stft(d_audio, N_SAMPLES_30S, d_n_valid, N_SAMPLES_30S, HOP, n_frames, B, m->mel, w.logmel.p,
-                                       w.max_key.p, m->stream));
-  if (want_bf16) {
-    const long long bs = static_cast<long long>(N_FRAMES_30S + 2) * nm;
-    WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.mel_bf16.p, bs, B, nm, m->stream));
-    WB_PROF(PC_OTHER, launch_fill_bf16_rows(w.mel_bf16.p + static_cast<long long>(N_FRAMES_30S + 1) * nm, bs, B, nm, m->stream));
-  }
-  WB_PROF(PC_MEL_FINALIZE, launch_mel_finalize(w.logmel.p, w.max_key.p, n_frames, N_FRAMES_30S, nm, B, d_mel_f32,
+  MelBatch job;
+  job.audio = d_audio; job.audio_stride = audio_stride; job.seg_off = d_seg_off; job.n_valid = d_n_valid; job.n_valid_all = N_SAMPLES_30S;
+  job.hop = HOP; job.B = B; job.n_frames = n_frames;
+  WB_PROF(PC_MEL_STFT, launch_mel_stft(job, m->mel, w.logmel.p, w.max_key.p, m->stream));
+  WB_PROF(PC_MEL_FINALIZE, launch_mel_finalize(w.logmel.p, w.max_key.p, w.mel_done.p, n_frames, N_FRAMES_30S, nm, B, d_mel_f32,
                                                want_bf16 ? w.mel_bf16.p : nullptr, m->stream));
   return WB_OK;
 }
@@ -160,40 +165,6 @@ int check_fused_dims(const Replica* m) {
 }
 
 
-// MelFilterbank::compute for one segment with the given filter tables (host in, host out).  Caller holds the model lock.
-int mel_compute_one(Replica* m, const MelTables& tab, const float* audio, size_t n, size_t hop, float* out, size_t out_capacity,
-                           size_t* n_frames_out) {
-  if (n_frames_out) *n_frames_out = 0;
-  if (n == 0) return WB_OK;                                                        // mel.rs:236-238
-  if (hop == 0) return set_error(WB_ERR_AUDIO, "hop_length must be positive");     // mel.rs:240-242
-  const size_t n_frames = n >= N_FFT ? (n - N_FFT) / hop + 1 : 0;                  // mel.rs:245-249
-  if (n_frames == 0) return WB_OK;
-  const int nm = tab.n_mels;
-  if (n > 0x7fff0000ull || hop > 0x7fff0000ull) return set_error(WB_ERR_AUDIO, "audio too long for one call");
-  if (!audio || !out || out_capacity < n_frames * nm) return set_error(WB_ERR_AUDIO, "output buffer too small");
-  DevBuf<float> d_audio, d_log, d_out;
-  DevBuf<int> d_key;
-  int rc;
-  auto cleanup = [&](int r) { d_audio.release(); d_log.release(); d_out.release(); d_key.release(); return r; };
-  if ((rc = d_audio.ensure((n + 3) & ~static_cast<size_t>(3))) != WB_OK) return cleanup(rc);
-  if ((rc = d_log.ensure(n_frames * nm)) != WB_OK) return cleanup(rc);
-  if ((rc = d_out.ensure(n_frames * nm)) != WB_OK) return cleanup(rc);
-  if ((rc = d_key.ensure(1)) != WB_OK) return cleanup(rc);
-  if (cudaMemcpyAsync(d_audio.p, audio, n * 4, cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
-    return cleanup(set_error(WB_ERR_CUDA, "H2D audio copy failed"));
-  rc = launch_mel_stft(d_audio.p, static_cast<long long>(d_audio.n), nullptr, static_cast<int>(n), static_cast<int>(hop),
-                       static_cast<int>(n_frames), 1, tab, d_log.p, d_key.p, m->stream);
-  if (rc != WB_OK) return cleanup(rc);
-  rc = launch_mel_finalize(d_log.p, d_key.p, static_cast<int>(n_frames), static_cast<int>(n_frames), nm, 1, d_out.p, nullptr, m->stream);
-  if (rc != WB_OK) return cleanup(rc);
-  if (cudaMemcpyAsync(out, d_out.p, n_frames * nm * 4, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess ||
-      cudaStreamSynchronize(m->stream) != cudaSuccess)
-    return cleanup(set_error(WB_ERR_CUDA, std::string("mel kernels failed: ") + cudaGetErrorString(cudaGetLastError())));
-  if (n_frames_out) *n_frames_out = n_frames;
-  return cleanup(WB_OK);
-}
-
-
 int compute_mel_host(Replica* m, const float* const* audio, const size_t* n_samples, const float* contiguous, int B,
                             float* out) {
   const int nm = m->mel.n_mels;
@@ -210,7 +181,7 @@ int compute_mel_host(Replica* m, const float* const* audio, const size_t* n_samp
       if (n) WB_CUDA_OK(cudaMemcpyAsync(m->ws.audio.p + static_cast<size_t>(i) * N_SAMPLES_30S, src, n * 4, cudaMemcpyHostToDevice, m->stream));
     }
     WB_CUDA_OK(cudaMemcpyAsync(m->ws.n_valid.p, nv.data(), nb * sizeof(int), cudaMemcpyHostToDevice, m->stream));
-    if ((rc = mel_device(m, m->ws.audio.p, m->ws.n_valid.p, nb, m->ws.mel_f32.p, false)) != WB_OK) return rc;
+    if ((rc = mel_device(m, m->ws.audio.p, N_SAMPLES_30S, nullptr, m->ws.n_valid.p, nb, m->ws.mel_f32.p, false)) != WB_OK) return rc;
     WB_CUDA_OK(cudaMemcpyAsync(out + static_cast<size_t>(b0) * per_out, m->ws.mel_f32.p, nb * per_out * 4, cudaMemcpyDeviceToHost, m->stream));
     WB_CUDA_OK(cudaStreamSynchronize(m->stream));     // nv goes out of scope; out is host-visible
   }
@@ -266,16 +237,19 @@ int validate_mel_len(const Replica* m, size_t mel_len, int* T_out) {
 
 
 // One fused mel + encoder step on the model's stream, replayed from a CUDA graph once its (pointers, batch) key has been seen twice.
-int mel_encode_step(Replica* m, const float* d_audio, const int* d_n_valid, int nb, void* d_out, wb_dtype out_dtype) {
+int mel_encode_step(Replica* m, const float* d_audio, long long audio_stride, const long long* d_seg_off, const int* d_n_valid, int nb,
+                    void* d_out, wb_dtype out_dtype) {
   auto eager = [&]() -> int {
-    int rc = mel_device(m, d_audio, d_n_valid, nb, nullptr, true);
+    int rc = mel_device(m, d_audio, audio_stride, d_seg_off, d_n_valid, nb, nullptr, true);
     if (rc != WB_OK) return rc;
     return encode_device(m, nb, N_FRAMES_30S, d_out, out_dtype, -1, true);
   };
   if (!m->use_graphs || m->prof_on) return eager();
   Replica::StepGraph* g = nullptr;
   for (auto& e : m->graphs)
-    if (e.in == d_audio && e.n_valid == d_n_valid && e.out == d_out && e.B == nb && e.dtype == static_cast<int>(out_dtype)) g = &e;
+    if (e.in == d_audio && e.n_valid == d_n_valid && e.seg_off == d_seg_off && e.stride == audio_stride && e.out == d_out && e.B == nb &&
+        e.dtype == static_cast<int>(out_dtype))
+      g = &e;
   if (!g) {
     if (m->graphs.size() >= 16) {                         // callers that never repeat their pointers do not accumulate graphs
       for (auto& e : m->graphs)
@@ -283,7 +257,7 @@ int mel_encode_step(Replica* m, const float* d_audio, const int* d_n_valid, int 
       m->graphs.clear();
     }
     Replica::StepGraph e;
-    e.in = d_audio; e.n_valid = d_n_valid; e.out = d_out; e.B = nb; e.dtype = static_cast<int>(out_dtype); e.seen = 1;
+    e.in = d_audio; e.n_valid = d_n_valid; e.seg_off = d_seg_off; e.stride = audio_stride; e.out = d_out; e.B = nb; e.dtype = static_cast<int>(out_dtype); e.seen = 1;
     m->graphs.push_back(e);
     return eager();
   }
@@ -368,7 +342,7 @@ int enqueue_microbatch(Replica* m, const float* const* audio, const size_t* n_sa
   WB_CUDA_OK(cudaEventRecord(sl.in_done, m->in_stream));
   WB_CUDA_OK(cudaStreamWaitEvent(m->stream, sl.in_done, 0));
   void* d_out = d_out_final ? d_out_final : static_cast<void*>(sl.out.p);
-  if ((rc = mel_encode_step(m, sl.audio.p, sl.n_valid.p, nb, d_out, out_dtype)) != WB_OK) return rc;
+  if ((rc = mel_encode_step(m, sl.audio.p, N_SAMPLES_30S, nullptr, sl.n_valid.p, nb, d_out, out_dtype)) != WB_OK) return rc;
   WB_CUDA_OK(cudaEventRecord(sl.compute_done, m->stream));
   if (out_host) {
     WB_CUDA_OK(cudaStreamWaitEvent(m->out_stream, sl.compute_done, 0));
@@ -393,19 +367,86 @@ int sync_replica(Replica* m) {
   return WB_OK;
 }
 
-// BatchPreprocessor::process_batch (src/audio/batch.rs:157-176) on the device: every segment through MelFilterbank::compute with the
-// given tables, neither padded nor truncated.
+// BatchPreprocessor::process_batch (src/audio/batch.rs:157-176) on the device, and MelFilterbank::compute for one segment as its
+// B = 1 case: every segment through the mel with the given tables, neither padded nor truncated.  The whole ragged batch is ONE
+// upload (segments packed into an arena), ONE stft launch over a tile table, one in-place finalize and ONE download; the arena, the
+// log-mel rows and the host staging vectors belong to the replica and are reused from call to call.
 int mel_compute_ragged(Replica* m, const MelTables& tab, const float* const* audio, const size_t* n_samples, int B, size_t hop,
                        float* const* mels_out, const size_t* out_capacity, size_t* frame_counts, size_t* max_frames_out) {
-  size_t max_frames = 0;
+  if (max_frames_out) *max_frames_out = 0;
+  const int nm = tab.n_mels;
+  std::vector<long long> seg_off(B), row_off(B);
+  std::vector<int> n_valid(B), n_fr(B);
+  std::vector<int2> tiles;
+  long long arena = 0, rows = 0, max_rows = 0;
   for (int i = 0; i < B; ++i) {
+    const size_t n = n_samples[i];
     size_t nf = 0;
-    int rc = mel_compute_one(m, tab, audio[i], n_samples[i], hop, mels_out[i], out_capacity ? out_capacity[i] : 0, &nf);
-    if (rc != WB_OK) return rc;
+    if (n != 0) {                                                                      // mel.rs:236-238: empty audio -> empty result
+      if (hop == 0) return set_error(WB_ERR_AUDIO, "hop_length must be positive");     // mel.rs:240-242
+      nf = n >= N_FFT ? (n - N_FFT) / hop + 1 : 0;                                     // mel.rs:245-249
+      if (n > 0x7fff0000ull || hop > 0x7fff0000ull || nf > 0x7fff0000ull) return set_error(WB_ERR_AUDIO, "audio too long for one call");
+      if (nf && (!audio[i] || !mels_out[i] || out_capacity[i] < nf * nm)) return set_error(WB_ERR_AUDIO, "output buffer too small");
+    }
     if (frame_counts) frame_counts[i] = nf;
-    max_frames = std::max(max_frames, nf);
+    n_fr[i] = static_cast<int>(nf);
+    n_valid[i] = static_cast<int>(n);
+    seg_off[i] = arena;
+    row_off[i] = rows;
+    if (nf) {
+      arena += static_cast<long long>((n + 3) & ~static_cast<size_t>(3));              // every segment starts 16 B aligned
+      rows += static_cast<long long>(nf);
+      max_rows = std::max<long long>(max_rows, static_cast<long long>(nf));
+      for (size_t f0 = 0; f0 < nf; f0 += 32) tiles.push_back(make_int2(i, static_cast<int>(f0)));
+    }
   }
-  if (max_frames_out) *max_frames_out = max_frames;
+  if (max_frames_out) *max_frames_out = static_cast<size_t>(max_rows);
+  if (rows == 0) return WB_OK;
+  int rc;
+  Replica::Ragged& r = m->rag;
+  if ((rc = r.audio.ensure(static_cast<size_t>(arena) + 4)) != WB_OK || (rc = r.logmel.ensure(static_cast<size_t>(rows) * nm)) != WB_OK ||
+      (rc = r.keys.ensure(B)) != WB_OK)
+    return rc;
+  // one table blob: seg_off | row_off | n_valid | n_frames | tiles
+  const size_t t_bytes = static_cast<size_t>(B) * (8 + 8 + 4 + 4) + tiles.size() * sizeof(int2) + 64;
+  if ((rc = r.tables.ensure(t_bytes)) != WB_OK) return rc;
+  r.h_tables.resize(t_bytes);
+  uint8_t* hb = r.h_tables.data();
+  size_t o_seg = 0, o_row = o_seg + 8 * static_cast<size_t>(B), o_nv = o_row + 8 * static_cast<size_t>(B), o_nf = o_nv + 4 * static_cast<size_t>(B);
+  size_t o_tiles = (o_nf + 4 * static_cast<size_t>(B) + 7) & ~static_cast<size_t>(7);
+  memcpy(hb + o_seg, seg_off.data(), 8 * static_cast<size_t>(B));
+  memcpy(hb + o_row, row_off.data(), 8 * static_cast<size_t>(B));
+  memcpy(hb + o_nv, n_valid.data(), 4 * static_cast<size_t>(B));
+  memcpy(hb + o_nf, n_fr.data(), 4 * static_cast<size_t>(B));
+  memcpy(hb + o_tiles, tiles.data(), tiles.size() * sizeof(int2));
+  r.h_audio.resize(static_cast<size_t>(arena));
+  for (int i = 0; i < B; ++i)
+    if (n_fr[i]) memcpy(r.h_audio.data() + seg_off[i], audio[i], static_cast<size_t>(n_valid[i]) * 4);
+  cudaStream_t st = m->stream;
+  WB_CUDA_OK(cudaMemcpyAsync(r.audio.p, r.h_audio.data(), static_cast<size_t>(arena) * 4, cudaMemcpyHostToDevice, st));
+  WB_CUDA_OK(cudaMemcpyAsync(r.tables.p, hb, t_bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_mel_init_keys(r.keys.p, B, st)) != WB_OK) return rc;
+  MelBatch job;
+  job.audio = r.audio.p;
+  job.seg_off = reinterpret_cast<const long long*>(r.tables.p + o_seg);
+  job.row_off = reinterpret_cast<const long long*>(r.tables.p + o_row);
+  job.n_valid = reinterpret_cast<const int*>(r.tables.p + o_nv);
+  job.n_frames_arr = reinterpret_cast<const int*>(r.tables.p + o_nf);
+  job.tiles = reinterpret_cast<const int2*>(r.tables.p + o_tiles);
+  job.n_tiles = static_cast<int>(tiles.size());
+  job.hop = static_cast<int>(hop);
+  job.B = B;
+  {
+    NvtxRange nvtx("step_f_mel");
+    WB_PROF(PC_MEL_STFT, launch_mel_stft(job, tab, r.logmel.p, r.keys.p, st));
+    WB_PROF(PC_MEL_FINALIZE, launch_mel_finalize_ragged(r.logmel.p, r.keys.p, job.n_frames_arr, job.row_off, nm, B, max_rows, r.logmel.p, st));
+  }
+  r.h_out.resize(static_cast<size_t>(rows) * nm);
+  if (cudaMemcpyAsync(r.h_out.data(), r.logmel.p, r.h_out.size() * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return set_error(WB_ERR_CUDA, std::string("mel kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
+  for (int i = 0; i < B; ++i)
+    if (n_fr[i]) memcpy(mels_out[i], r.h_out.data() + row_off[i] * nm, static_cast<size_t>(n_fr[i]) * nm * 4);
   return WB_OK;
 }
 

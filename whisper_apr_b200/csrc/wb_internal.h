@@ -108,12 +108,35 @@ struct MelTables {                 // device-resident, built at model load
   const int* span_off;
   int nnz;
 };
-// logmel[b][f][j] = log10(max(E,1e-10)) for f < n_frames; chunk_max_key[b] = ordered-int max.
-int launch_mel_stft(const float* audio, long long audio_stride, const int* n_valid, int padded_len, int hop, int n_frames,
-                    int B, const MelTables& t, float* logmel, int* chunk_max_key, cudaStream_t stream);
-// clamp/scale/pad: out_f32 [B][T_out][m] (optional), out_bf16 [B][T_out+2][m] with zero pad rows (optional)
-int launch_mel_finalize(const float* logmel, const int* chunk_max_key, int n_frames, int T_out, int n_mels, int B,
+// What one mel launch processes.  Regular form: B segments at `audio + b * audio_stride`, n_frames frames each, log-mel rows
+// b * n_frames ...  Ragged / view form: per-segment device tables -- seg_off (element offset of the segment's first sample: lets
+// chunks be overlapping VIEWS into longer streams), n_valid (samples that exist; later ones read as 0: compute_mel's zero padding),
+// n_frames_arr, row_off (first log-mel row) -- and a tile table {segment, first frame} with one entry per 32-frame tile.
+struct MelBatch {
+  const float* audio = nullptr;
+  long long audio_stride = 0;
+  const long long* seg_off = nullptr;
+  const int* n_valid = nullptr;
+  int n_valid_all = 0;
+  int hop = 160;
+  int B = 0;
+  int n_frames = 0;
+  const int* n_frames_arr = nullptr;
+  const long long* row_off = nullptr;
+  const int2* tiles = nullptr;
+  int n_tiles = 0;
+};
+// logmel[row][j] = log10(max(E,1e-10)); chunk_max_key[b] = ordered-int max (must hold key(-inf) on entry: launch_mel_init_keys once,
+// launch_mel_finalize re-arms it).
+int launch_mel_stft(const MelBatch& job, const MelTables& t, float* logmel, int* chunk_max_key, cudaStream_t stream);
+int launch_mel_init_keys(int* keys, int B, cudaStream_t stream);
+// clamp/scale/pad: out_f32 [B][T_out][m] (optional), out_bf16 [B][T_out+2][m] with its two zero guard rows (optional).
+// done_counter: [B] zero-initialised scratch of the "last block re-arms the key" protocol.
+int launch_mel_finalize(const float* logmel, int* chunk_max_key, unsigned int* done_counter, int n_frames, int T_out, int n_mels, int B,
                         float* out_f32, __nv_bfloat16* out_bf16_padded, cudaStream_t stream);
+// ragged segments, in place allowed (out may alias logmel); keys are NOT re-armed
+int launch_mel_finalize_ragged(const float* logmel, const int* max_keys, const int* n_frames_arr, const long long* row_off, int n_mels, int B,
+                               long long max_rows, float* out, cudaStream_t stream);
 int mel_init();
 
 // ---- elementwise / normalisation
