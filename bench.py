@@ -6,7 +6,7 @@
 
 A "step" is one pass of the hot path (log-mel of 30 s chunks + Whisper encoder forward) over one batch of synthetic
 chunks per GPU.  Workload at every N: whisper-large-v3 shape (128 mel, 32 layers, d = 1280), bf16 tensor-core math with
-fp32 accumulation / residual stream, 32 chunks per GPU per step (BASELINE.json configs[3]: 256 chunks over 8 GPUs), random-init
+fp32 accumulation / residual stream (16-bit operands: fp16 by default), 32 chunks per GPU per step (BASELINE.json configs[3]: 256 chunks over 8 GPUs), random-init
 weights serialised through the `.apr` v1 writer, synthetic audio.  Weak scaling: per-GPU work is fixed, chunks shard by
 batch, no data-path collective.
 
@@ -181,8 +181,8 @@ def run_reference(args, rank: int, world: int):
 
 
 def workload_name(args):
-    return {"large-v3": "whisper-large-v3 shape (128 mel, 32 enc layers, d=1280) bf16, 30 s chunks sharded by batch",
-            }.get(args.model, f"whisper-{args.model} shape bf16, 30 s chunks sharded by batch")
+    return {"large-v3": "whisper-large-v3 shape (128 mel, 32 enc layers, d=1280), 16-bit tensor-core operands, 30 s chunks sharded by batch",
+            }.get(args.model, f"whisper-{args.model} shape, 16-bit tensor-core operands, 30 s chunks sharded by batch")
 
 
 
@@ -440,7 +440,9 @@ def main():
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+               "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": lib.wb_operand_format().decode(), "dtype_note": "16-bit tensor-core operands (IEEE fp16 unless built with -DWB_OPERANDS_BF16), fp32 "
+               "accumulation, fp32 residual stream and LayerNorm statistics; same tcgen05 kind::f16 rate and bytes as bf16 (DESIGN.md section 4)",
                "data": "synthetic",
                "config": make_config(args, world),
                "setup": {"load_s": round(load_s, 2), "apr_mb": round(apr_mb), "synth_and_load_s": round(setup_s, 1),

@@ -56,7 +56,7 @@ typedef struct wb_config {
   uint32_t n_tensors;
 } wb_config;
 
-/* Output element type of the fused batch entry point. */
+/* Output element type of the fused batch entry point (a storage format for the caller; independent of the operand format). */
 typedef enum wb_dtype { WB_F32 = 0, WB_BF16 = 1 } wb_dtype;
 
 /* On-device requantisation modes of wb_model_requantize. */
@@ -64,6 +64,8 @@ typedef enum wb_dtype { WB_F32 = 0, WB_BF16 = 1 } wb_dtype;
 
 /* ---- library ---------------------------------------------------------------------- */
 const char* wb_version(void);
+/* "fp16" or "bf16": the 16-bit format of every tensor-core operand in this build (IEEE fp16 by default). */
+const char* wb_operand_format(void);
 /* WhisperError Display (src/error.rs).  Thread-local; valid until the next failing call. */
 const char* wb_last_error(void);
 /* parallel::thread_count (src/parallel.rs:155-170) -> number of visible CUDA devices. */

@@ -48,7 +48,9 @@ def test_cross_kv_precompute_matches_oracle(tiny_full):
     enc = rng.standard_normal((1500, cfg.n_text_state)).astype(np.float32)
     d = cfg.n_text_state
     import torch
-    r = lambda x: torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.bfloat16).to(torch.float64).numpy()
+    from whisper_apr_b200 import _lib
+    t16 = torch.float16 if _lib.lib().wb_operand_format() == b"fp16" else torch.bfloat16
+    r = lambda x: torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(t16).to(torch.float64).numpy()
     for layer in (0, cfg.n_text_layer - 1):
         k, v = model.debug_cross_kv(enc, layer)
         p = f"decoder.layers.{layer}.encoder_attn"

@@ -26,8 +26,10 @@ def _p(a):
 
 
 def _bf16_round(x):
+    """Round to the library's 16-bit OPERAND format (fp16 by default, bf16 in a -DWB_OPERANDS_BF16 build)."""
     import torch
-    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+    t = torch.float16 if _lib.lib().wb_operand_format() == b"fp16" else torch.bfloat16
+    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(t).to(torch.float32).numpy()
 
 
 def _cos(a, b):

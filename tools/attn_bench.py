@@ -15,7 +15,7 @@ for (B, S, d, H) in [(1, 128, 64, 1), (2, 300, 128, 2), (1, 1500, 384, 6)]:
     out = np.empty((B, S, d), np.float32)
     _lib.check(L.wb_debug_attention(0, _p(qkv), B, S, d, H, _p(out)))
     import torch
-    q16 = torch.from_numpy(qkv).to(torch.bfloat16).to(torch.float64).numpy()
+    q16 = torch.from_numpy(qkv).to(torch.float16 if L.wb_operand_format() == b'fp16' else torch.bfloat16).to(torch.float64).numpy()
     ref = np.empty((B, S, d))
     for b in range(B):
         for h in range(H):

@@ -30,6 +30,7 @@ _vp = C.c_void_p
 # name -> (restype, argtypes): every symbol include/whisper_b200.h declares
 SIGNATURES = {
     "wb_version": (C.c_char_p, []),
+    "wb_operand_format": (C.c_char_p, []),
     "wb_last_error": (C.c_char_p, []),
     "wb_device_count": (C.c_int, []),
     "wb_model_from_apr": (C.c_int, [_vp, C.c_size_t, C.c_int, C.POINTER(_vp)]),

@@ -50,7 +50,7 @@ int enable_peer(Replica* from, int to_device) {
 // d_out: device buffer on replica `out_rep` (peer stores from the others), or nullptr.
 int sharded_enqueue(wb_model* h, const float* const* audio, const size_t* n_samples, int B, void* out_host, void* d_out, wb_dtype dt) {
   const int G = static_cast<int>(h->reps.size());
-  const size_t d = h->cfg.n_audio_state, per = static_cast<size_t>(N_POS_30S) * d * (dt == WB_BF16 ? 2 : 4);
+  const size_t d = h->cfg.n_audio_state, per = static_cast<size_t>(N_POS_30S) * d * dtype_size(dt);
   std::vector<int> pos(G), end(G);
   for (int g = 0; g < G; ++g) shard_range(B, G, g, &pos[g], &end[g]);
   bool more = true;
@@ -81,7 +81,8 @@ using namespace wb;
 // =====================================================================================================
 extern "C" {
 
-const char* wb_version(void) { return "whisper_b200 0.2.0 (sm_100a)"; }
+const char* wb_version(void) { return kOp16IsFp16 ? "whisper_b200 0.2.0 (sm_100a, fp16 operands)" : "whisper_b200 0.2.0 (sm_100a, bf16 operands)"; }
+const char* wb_operand_format(void) { return kOp16IsFp16 ? "fp16" : "bf16"; }
 const char* wb_last_error(void) { return wb::last_error(); }
 
 int wb_device_count(void) {
@@ -366,6 +367,7 @@ int wb_encode_batch(const wb_model* h, const float* const* mels, const size_t* m
 int wb_encode_batch_dev(const wb_model* h, const float* d_mel, int B, void* d_out, wb_dtype out_dtype) {
   Replica* m = rep0(h);
   if (!m || !d_mel || !d_out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
+  if (out_dtype != WB_F32 && out_dtype != WB_BF16) return set_error(WB_ERR_MODEL, "output dtype must be WB_F32 or WB_BF16");
   int rc = check_fused_dims(m);
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
@@ -377,11 +379,12 @@ int wb_encode_batch_dev(const wb_model* h, const float* d_mel, int B, void* d_ou
 int wb_mel_encode_batch_dev(const wb_model* h, const float* d_audio, int B, void* d_out, wb_dtype out_dtype) {
   Replica* m = rep0(h);
   if (!m || !d_audio || !d_out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
+  if (out_dtype != WB_F32 && out_dtype != WB_BF16) return set_error(WB_ERR_MODEL, "output dtype must be WB_F32 or WB_BF16");
   int rc = check_fused_dims(m);
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
-  const size_t d = m->cfg.n_audio_state, S = N_POS_30S, esz = out_dtype == WB_BF16 ? 2 : 4;
+  const size_t d = m->cfg.n_audio_state, S = N_POS_30S, esz = dtype_size(out_dtype);
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = std::min(m->max_batch, B - b0);
     if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
@@ -395,6 +398,7 @@ int wb_mel_encode_batch_dev(const wb_model* h, const float* d_audio, int B, void
 int wb_mel_encode_batch_async(const wb_model* ch, const float* const* audio, const size_t* n_samples, int B, void* out, wb_dtype out_dtype) {
   wb_model* h = const_cast<wb_model*>(ch);
   if (!rep0(h) || !audio || !n_samples || !out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
+  if (out_dtype != WB_F32 && out_dtype != WB_BF16) return set_error(WB_ERR_MODEL, "output dtype must be WB_F32 or WB_BF16");
   int rc = check_fused_dims(rep0(h));
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -418,10 +422,11 @@ int wb_mel_encode_gather(const wb_model* ch, const float* const* audio, const si
   if (!rep0(h) || !audio || !n_samples || !d_states_out || B < 0) return set_error(WB_ERR_MODEL, "null argument");
   const int G = static_cast<int>(h->reps.size());
   if (gather_index < 0 || gather_index >= G) return set_error(WB_ERR_MODEL, "gather index outside the handle's device list");
+  if (out_dtype != WB_F32 && out_dtype != WB_BF16) return set_error(WB_ERR_MODEL, "output dtype must be WB_F32 or WB_BF16");
   int rc = check_fused_dims(rep0(h));
   if (rc != WB_OK) return rc;
   std::lock_guard<std::mutex> lk(h->mu);
-  const size_t bytes = static_cast<size_t>(B) * N_POS_30S * h->cfg.n_audio_state * (out_dtype == WB_BF16 ? 2 : 4);
+  const size_t bytes = static_cast<size_t>(B) * N_POS_30S * h->cfg.n_audio_state * dtype_size(out_dtype);
   Replica* root = h->reps[gather_index];
   if (h->gather_dev_index != gather_index || h->gather_bytes < bytes) {
     if ((rc = wb_sync(h)) != WB_OK) return rc;                 // nobody may still be writing the old buffer
@@ -501,16 +506,16 @@ int wb_read_device(int device, const void* d_src, void* host_dst, size_t bytes) 
 
 // ------------------------------------------------------------------------------------------ decoder
 namespace {
-// host f32 states [B][S][d] -> bf16 on the replica's device (DecodeState::states is private to decoder.cu: use the workspace)
-int states_to_device_bf16(Replica* m, const float* states, size_t rows, DevBuf<float>& f32, DevBuf<bf16>& b16) {
+// host f32 states [B][S][d] -> op16 on the replica's device (DecodeState::states is private to decoder.cu: use the workspace)
+int states_to_device_bf16(Replica* m, const float* states, size_t rows, DevBuf<float>& f32, DevBuf<op16>& b16) {
   const size_t n = rows * m->cfg.n_audio_state;
   int rc;
   if ((rc = f32.ensure(n)) != WB_OK || (rc = b16.ensure(n)) != WB_OK) return rc;
   WB_CUDA_OK(cudaMemcpyAsync(f32.p, states, n * 4, cudaMemcpyHostToDevice, m->stream));
-  return launch_f32_to_bf16(f32.p, b16.p, n, m->stream);
+  return launch_f32_to_op16(f32.p, b16.p, n, m->stream);
 }
 
-// transcribe_batch_optimized steps 1-3 for one replica's shard: mel + encoder (bf16 states stay in HBM) -> cross K/V + greedy loop
+// transcribe_batch_optimized steps 1-3 for one replica's shard: mel + encoder (op16 states stay in HBM) -> cross K/V + greedy loop
 int transcribe_shard(Replica* m, const float* const* audio, const size_t* n_samples, int cnt, const int32_t* init, int n_init, int max_tokens,
                      int suppress_ts, int32_t* tokens_out, int32_t* lens_out) {
   std::lock_guard<std::mutex> lk(m->mu);
@@ -527,7 +532,7 @@ int transcribe_shard(Replica* m, const float* const* audio, const size_t* n_samp
       if (n) WB_CUDA_OK(cudaMemcpyAsync(m->ws.audio.p + static_cast<size_t>(i) * N_SAMPLES_30S, audio[b0 + i], n * 4, cudaMemcpyHostToDevice, m->stream));
     }
     WB_CUDA_OK(cudaMemcpy(m->ws.n_valid.p, nv.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
-    if ((rc = mel_encode_step(m, m->ws.audio.p, N_SAMPLES_30S, nullptr, m->ws.n_valid.p, nb, m->ws.out_bf16.p, WB_BF16)) != WB_OK) return rc;
+    if ((rc = mel_encode_step(m, m->ws.audio.p, N_SAMPLES_30S, nullptr, m->ws.n_valid.p, nb, m->ws.out_bf16.p, WB_OP16)) != WB_OK) return rc;
     if ((rc = decoder_greedy(m, m->ws.out_bf16.p, nb, init, n_init, max_tokens, suppress_ts, tokens_out + static_cast<size_t>(b0) * max_tokens,
                              lens_out + b0)) != WB_OK)
       return rc;
@@ -549,7 +554,7 @@ int wb_decode_greedy(const wb_model* h, const float* states, size_t seq_len, int
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
   DevBuf<float> f32;
-  DevBuf<bf16> b16;
+  DevBuf<op16> b16;
   const int step = 32;
   for (int b0 = 0; b0 < B; b0 += step) {
     const int nb = std::min(step, B - b0);
@@ -601,7 +606,7 @@ int wb_debug_decoder_logits(const wb_model* h, const float* states, size_t seq_l
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
   DevBuf<float> f32;
-  DevBuf<bf16> b16;
+  DevBuf<op16> b16;
   int rc = states_to_device_bf16(m, states, seq_len, f32, b16);
   if (rc != WB_OK) return rc;
   std::vector<int32_t> toks(n_tokens + 1);
@@ -615,7 +620,7 @@ int wb_debug_cross_kv(const wb_model* h, const float* states, size_t seq_len, in
   std::lock_guard<std::mutex> lk(m->mu);
   DeviceGuard guard(m->device);
   DevBuf<float> f32;
-  DevBuf<bf16> b16;
+  DevBuf<op16> b16;
   int rc = states_to_device_bf16(m, states, seq_len, f32, b16);
   if (rc != WB_OK) return rc;
   return decoder_debug_cross_kv(m, b16.p, static_cast<int>(seq_len), layer, k_out, v_out);

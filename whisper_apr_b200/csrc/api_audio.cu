@@ -220,6 +220,7 @@ int wb_stream_encode_views(const wb_model* ch, const float* const* streams, cons
   wb_model* h = const_cast<wb_model*>(ch);
   Replica* m0 = rep0(h);
   if (!m0 || n_streams < 0 || (n_streams > 0 && (!streams || !stream_lens))) return set_error(WB_ERR_MODEL, "null argument");
+  if (out_dtype != WB_F32 && out_dtype != WB_BF16) return set_error(WB_ERR_MODEL, "output dtype must be WB_F32 or WB_BF16");
   int rc = check_fused_dims(m0);
   if (rc != WB_OK) return rc;
   if (chunk_size > static_cast<size_t>(N_SAMPLES_30S)) return set_error(WB_ERR_AUDIO, "chunk size above 30 s (compute_mel would truncate it)");
@@ -235,7 +236,7 @@ int wb_stream_encode_views(const wb_model* ch, const float* const* streams, cons
   if (!out || out_capacity_chunks < total) return set_error(WB_ERR_MODEL, "output buffer too small");
   std::lock_guard<std::mutex> hl(h->mu);
   const int G = static_cast<int>(h->reps.size());
-  const size_t d = h->cfg.n_audio_state, per = static_cast<size_t>(N_POS_30S) * d * (out_dtype == WB_BF16 ? 2 : 4);
+  const size_t d = h->cfg.n_audio_state, per = static_cast<size_t>(N_POS_30S) * d * dtype_size(out_dtype);
   for (int g = 0; g < G; ++g) {
     const int s0 = static_cast<int>((static_cast<long long>(g) * n_streams + G - 1) / G);
     const int s1 = std::min<int>(n_streams, static_cast<int>((static_cast<long long>(g + 1) * n_streams + G - 1) / G));
@@ -280,7 +281,7 @@ int wb_stream_encode_views(const wb_model* ch, const float* const* streams, cons
     for (size_t c0 = 0; c0 < n_chunks; c0 += m->max_batch) {
       const int nb = static_cast<int>(std::min<size_t>(m->max_batch, n_chunks - c0));
       if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
-      void* d_o = out_dtype == WB_BF16 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
+      void* d_o = out_dtype != WB_F32 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
       if ((rc = mel_encode_step(m, r.audio.p, 0, d_off + c0, d_nv + c0, nb, d_o, out_dtype)) != WB_OK) return rc;
       WB_CUDA_OK(cudaMemcpyAsync(dst + c0 * per, d_o, static_cast<size_t>(nb) * per, cudaMemcpyDeviceToHost, st));
     }
@@ -374,6 +375,7 @@ int wb_stream_set_encode(wb_stream_set* s, int flush, void* out, wb_dtype out_dt
   if (!s || !n_chunks_out) return set_error(WB_ERR_MODEL, "null argument");
   *n_chunks_out = 0;
   Replica* m = rep0(s->model);
+  if (out_dtype != WB_F32 && out_dtype != WB_BF16) return set_error(WB_ERR_MODEL, "output dtype must be WB_F32 or WB_BF16");
   int rc = check_fused_dims(m);
   if (rc != WB_OK) return rc;
   std::vector<int2> ready;
@@ -390,11 +392,11 @@ int wb_stream_set_encode(wb_stream_set* s, int flush, void* out, wb_dtype out_dt
   if ((rc = launch_assemble_chunks(s->ready.p, n, s->acc.p, s->acc_stride, s->chunk_samples, s->overlap_samples, s->chunks.p, s->chunk_stride,
                                    s->n_valid.p, st)) != WB_OK)
     return rc;
-  const size_t d = m->cfg.n_audio_state, per = static_cast<size_t>(N_POS_30S) * d * (out_dtype == WB_BF16 ? 2 : 4);
+  const size_t d = m->cfg.n_audio_state, per = static_cast<size_t>(N_POS_30S) * d * dtype_size(out_dtype);
   for (int c0 = 0; c0 < n; c0 += m->max_batch) {
     const int nb = std::min(m->max_batch, n - c0);
     if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
-    void* d_o = out_dtype == WB_BF16 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
+    void* d_o = out_dtype != WB_F32 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
     if ((rc = mel_encode_step(m, s->chunks.p + static_cast<long long>(c0) * s->chunk_stride, s->chunk_stride, nullptr, s->n_valid.p + c0, nb, d_o,
                               out_dtype)) != WB_OK)
       return rc;

@@ -48,7 +48,7 @@ struct AttnTmParams {
   int S, d, n_kv_blocks;
   int n_qpairs, n_heads, n_items;     // work items = B * n_heads * n_qpairs, q-pair fastest (neighbours share K/V through L2)
   float scale_log2;
-  __nv_bfloat16* out;
+  op16* out;
   int use_token;
 };
 
@@ -87,7 +87,7 @@ __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk
     const float e0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), c, -mb));         // exp2(-inf) == 0: masked keys contribute nothing
     const float e1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), c, -mb));
     rs4[i & 3] += e0 + e1;
-    pk[i] = pack_bf16x2(e0, e1);
+    pk[i] = pack_op16x2(e0, e1);
   }
   return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 }
@@ -159,7 +159,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
     } else if (warp == 1) {
       if (lane == 0) {
         // ------------------------------------------------------------------ S_t = Q_t K^T issuer (both tiles)
-        constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0);
+        constexpr uint32_t idesc_s = umma_idesc_op16(BQ, BKV, 0);
         uint32_t g = 0;
         int it = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
@@ -187,7 +187,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
     } else {
       if (lane == 0) {
         // ------------------------------------------------------------------ O_t += P_t V issuer, one warp per tile
-        constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, 1);        // B = V tile, MN-major
+        constexpr uint32_t idesc_o = umma_idesc_op16(BQ, DH, 1);        // B = V tile, MN-major
         const int t = warp - 2;
         const uint32_t tO = tmem_base + COL_O + t * 64;
         const uint32_t tP = tmem_base + COL_P + t * 64;
@@ -304,10 +304,10 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
 #pragma unroll
           for (int gg = 0; gg < 4; ++gg) {
             uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(v[8 * gg + 0]) * inv, __uint_as_float(v[8 * gg + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(v[8 * gg + 2]) * inv, __uint_as_float(v[8 * gg + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(v[8 * gg + 4]) * inv, __uint_as_float(v[8 * gg + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(v[8 * gg + 6]) * inv, __uint_as_float(v[8 * gg + 7]) * inv);
+            w.x = pack_op16x2(__uint_as_float(v[8 * gg + 0]) * inv, __uint_as_float(v[8 * gg + 1]) * inv);
+            w.y = pack_op16x2(__uint_as_float(v[8 * gg + 2]) * inv, __uint_as_float(v[8 * gg + 3]) * inv);
+            w.z = pack_op16x2(__uint_as_float(v[8 * gg + 4]) * inv, __uint_as_float(v[8 * gg + 5]) * inv);
+            w.w = pack_op16x2(__uint_as_float(v[8 * gg + 6]) * inv, __uint_as_float(v[8 * gg + 7]) * inv);
             dst[cc * 4 + gg] = w;
           }
         }
@@ -334,13 +334,13 @@ int attention_init() {
   });
 }
 
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream) {
+int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream) {
   int rc = attention_init();
   if (rc != WB_OK) return rc;
   if (B <= 0 || S <= 0) return WB_OK;
   if (d != n_heads * DH) return set_error(WB_ERR_MODEL, "attention kernel needs d_head == 64 (all Whisper sizes)");
   CUtensorMap tm;      // one map serves Q, K and V tiles: box = 64 columns x 128 rows of the [B][S][3d] qkv buffer
-  rc = make_tmap_bf16_3d(&tm, qkv, 3ull * d, S, B, 3ull * d * 2, 3ull * d * 2 * S, DH, BQ);
+  rc = make_tmap_op16_3d(&tm, qkv, 3ull * d, S, B, 3ull * d * 2, 3ull * d * 2 * S, DH, BQ);
   if (rc != WB_OK) return rc;
   AttnTmParams p;
   p.S = S;

@@ -24,7 +24,7 @@ int wb_debug_gemm(int device, const float* A, const float* W, const float* bias,
   int rc = debug_device(device);
   if (rc != WB_OK) return rc;
   DevBuf<float> fa, fw, fb, fo, fpe;
-  DevBuf<bf16> ba, bw, bo;
+  DevBuf<op16> ba, bw, bo;
   auto cleanup = [&](int r) { fa.release(); fw.release(); fb.release(); fo.release(); fpe.release(); ba.release(); bw.release(); bo.release(); return r; };
   const size_t na = static_cast<size_t>(M) * K, nw = static_cast<size_t>(N) * K, no = static_cast<size_t>(M) * N;
   if ((rc = fa.ensure(na)) || (rc = fw.ensure(nw)) || (rc = fo.ensure(no)) || (rc = ba.ensure(na)) || (rc = bw.ensure(nw)) ||
@@ -33,8 +33,8 @@ int wb_debug_gemm(int device, const float* A, const float* W, const float* bias,
   cudaMemcpy(fa.p, A, na * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(fw.p, W, nw * 4, cudaMemcpyHostToDevice);
   if (bias) cudaMemcpy(fb.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice);
-  launch_f32_to_bf16(fa.p, ba.p, na, nullptr);
-  launch_f32_to_bf16(fw.p, bw.p, nw, nullptr);
+  launch_f32_to_op16(fa.p, ba.p, na, nullptr);
+  launch_f32_to_op16(fw.p, bw.p, nw, nullptr);
   GemmDesc g{};
   g.A = ba.p; g.a_row_stride = K; g.a_batch_stride = static_cast<long long>(M) * K; g.rows_per_batch = M; g.n_batch = 1;
   g.W = bw.p; g.N = N; g.K = K; g.epilogue = epilogue; g.alpha = alpha; g.col_scale = nullptr; g.bias = bias ? fb.p : nullptr;
@@ -53,9 +53,9 @@ int wb_debug_gemm(int device, const float* A, const float* W, const float* bias,
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("gemm kernel failed: ") + cudaGetErrorString(e)));
   if (bf_out) {
-    std::vector<bf16> h(no);
+    std::vector<op16> h(no);
     cudaMemcpy(h.data(), bo.p, no * 2, cudaMemcpyDeviceToHost);
-    for (size_t i = 0; i < no; ++i) out[i] = __bfloat162float(h[i]);
+    for (size_t i = 0; i < no; ++i) out[i] = op16_to_float(h[i]);
   } else {
     cudaMemcpy(out, fo.p, no * 4, cudaMemcpyDeviceToHost);
   }
@@ -66,18 +66,18 @@ int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_
   int rc = debug_device(device);
   if (rc != WB_OK) return rc;
   DevBuf<float> f;
-  DevBuf<bf16> bq, bo;
+  DevBuf<op16> bq, bo;
   auto cleanup = [&](int r) { f.release(); bq.release(); bo.release(); return r; };
   const size_t nq = static_cast<size_t>(B) * S * 3 * d, no = static_cast<size_t>(B) * S * d;
   if ((rc = f.ensure(nq)) || (rc = bq.ensure(nq)) || (rc = bo.ensure(no))) return cleanup(rc);
   cudaMemcpy(f.p, qkv, nq * 4, cudaMemcpyHostToDevice);
-  launch_f32_to_bf16(f.p, bq.p, nq, nullptr);
+  launch_f32_to_op16(f.p, bq.p, nq, nullptr);
   if ((rc = launch_attention(bq.p, bo.p, B, S, d, n_heads, nullptr)) != WB_OK) return cleanup(rc);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("attention kernel failed: ") + cudaGetErrorString(e)));
-  std::vector<bf16> h(no);
+  std::vector<op16> h(no);
   cudaMemcpy(h.data(), bo.p, no * 2, cudaMemcpyDeviceToHost);
-  for (size_t i = 0; i < no; ++i) out[i] = __bfloat162float(h[i]);
+  for (size_t i = 0; i < no; ++i) out[i] = op16_to_float(h[i]);
   return cleanup(WB_OK);
 }
 
@@ -86,7 +86,7 @@ int wb_debug_gemm_bench(int device, int n_batch, int rows, int N, int K, int epi
   if (rc != WB_OK) return rc;
   if (!ms_per_launch || iters <= 0) return set_error(WB_ERR_MODEL, "bad argument");
   DevBuf<float> f, fb, fo;
-  DevBuf<bf16> ba, bw, bo;
+  DevBuf<op16> ba, bw, bo;
   auto cleanup = [&](int r) { f.release(); fb.release(); fo.release(); ba.release(); bw.release(); bo.release(); return r; };
   const size_t M = static_cast<size_t>(n_batch) * rows, na = M * K, nw = static_cast<size_t>(N) * K, no = M * N;
   const size_t nf = std::max(static_cast<size_t>(rows) * K, nw);
@@ -102,8 +102,8 @@ int wb_debug_gemm_bench(int device, int n_batch, int rows, int N, int K, int epi
   }
   cudaMemcpy(f.p, h.data(), nf * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(fb.p, h.data(), static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice);
-  launch_f32_to_bf16(f.p, bw.p, nw, nullptr);
-  launch_f32_to_bf16(f.p, ba.p, static_cast<size_t>(rows) * K, nullptr);
+  launch_f32_to_op16(f.p, bw.p, nw, nullptr);
+  launch_f32_to_op16(f.p, ba.p, static_cast<size_t>(rows) * K, nullptr);
   for (int b = 1; b < n_batch; ++b)
     cudaMemcpyAsync(ba.p + static_cast<size_t>(b) * rows * K, ba.p, static_cast<size_t>(rows) * K * 2, cudaMemcpyDeviceToDevice, nullptr);
   if (!bf_out) cudaMemsetAsync(fo.p, 0, no * 4, nullptr);
@@ -135,7 +135,7 @@ int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int i
   if (rc != WB_OK) return rc;
   if (!ms_per_launch || iters <= 0) return set_error(WB_ERR_MODEL, "bad argument");
   DevBuf<float> f;
-  DevBuf<bf16> bq, bo;
+  DevBuf<op16> bq, bo;
   auto cleanup = [&](int r) { f.release(); bq.release(); bo.release(); return r; };
   const size_t per = static_cast<size_t>(S) * 3 * d, nq = per * B, no = static_cast<size_t>(B) * S * d;
   if ((rc = f.ensure(per)) || (rc = bq.ensure(nq)) || (rc = bo.ensure(no))) return cleanup(rc);
@@ -146,7 +146,7 @@ int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int i
     h[i] = (static_cast<float>(x >> 8) / 8388608.0f - 1.0f) * 2.0f;
   }
   cudaMemcpy(f.p, h.data(), per * 4, cudaMemcpyHostToDevice);
-  launch_f32_to_bf16(f.p, bq.p, per, nullptr);
+  launch_f32_to_op16(f.p, bq.p, per, nullptr);
   for (int b = 1; b < B; ++b) cudaMemcpyAsync(bq.p + b * per, bq.p, per * 2, cudaMemcpyDeviceToDevice, nullptr);
   EventPair ev;
   cudaEvent_t e0 = ev.e0, e1 = ev.e1;
@@ -229,7 +229,7 @@ int wb_debug_layernorm(int device, const float* x, const float* gamma, const flo
   cudaMemcpy(fx.p, x, n * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(fg.p, gamma, static_cast<size_t>(d) * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(fb.p, beta, static_cast<size_t>(d) * 4, cudaMemcpyHostToDevice);
-  if ((rc = launch_layernorm(fx.p, fg.p, fb.p, rows, d, nullptr, fo.p, nullptr)) != WB_OK) return cleanup(rc);
+  if ((rc = launch_layernorm(fx.p, fg.p, fb.p, rows, d, nullptr, false, fo.p, nullptr)) != WB_OK) return cleanup(rc);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return cleanup(set_error(WB_ERR_CUDA, std::string("layernorm kernel failed: ") + cudaGetErrorString(e)));
   cudaMemcpy(out, fo.p, n * 4, cudaMemcpyDeviceToHost);

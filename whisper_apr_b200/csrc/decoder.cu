@@ -4,7 +4,7 @@
 // Replaces, for B chunks decoded side by side:
 //   Decoder::forward_one / forward_block_cached / compute_attention_cached     src/model/decoder.rs:2125-2172, 2241-2325, 2414-2459
 //     (the non-cached path recomputes the encoder K/V projections per token, decoder.rs:2017-2040; the cached path computes them on the
-//      first token -- here they are two tcgen05 GEMMs per layer straight from the encoder's bf16 output buffer)
+//      first token -- here they are two tcgen05 GEMMs per layer straight from the encoder's op16 output buffer)
 //   Decoder::project_to_vocab (weight-tied logits)                             src/model/decoder.rs:1794-1806
 //   WhisperApr::decode (feed unseen tokens, suppress, pick)                    src/lib.rs:529-598
 //   WhisperTokenSuppressor::{new, apply}                                       src/inference/processors.rs:60-147
@@ -12,7 +12,7 @@
 //
 // Precision: the per-token path is f32 end to end (f32 weights, f32 KV cache, f32 logits) -- one row per chunk, so it is bound by
 // weight bandwidth and launch latency, not by math, and f32 keeps the argmax on the reference's side of every near-tie.  Only the
-// cross-attention K/V (B x 1500 rows per layer, the GEMM-shaped part) are bf16 tensor-core outputs.
+// cross-attention K/V (B x 1500 rows per layer, the GEMM-shaped part) are op16 tensor-core outputs.
 #include "loader.h"
 #include "ptx.cuh"
 
@@ -20,8 +20,8 @@ namespace wb {
 
 struct DecodeState {
   int cap_B = 0, cap_S = 0, cap_T = 0;
-  DevBuf<bf16> states;         // [B*S][d]   bf16 copy of host-supplied states
-  DevBuf<bf16> kv_cross;       // [L][B*S][2d]
+  DevBuf<op16> states;         // [B*S][d]   op16 copy of host-supplied states
+  DevBuf<op16> kv_cross;       // [L][B*S][2d]
   DevBuf<float> kv_self;       // [L][B][T][2d]
   DevBuf<float> x, xn, qkv, att, hid, q, logits;
   DevBuf<int> tokens;          // [B][T]
@@ -215,9 +215,9 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
   if (tid < DH) out[static_cast<size_t>(b) * d + h * DH + tid] = (part[0][tid] + part[1][tid]) * inv;
 }
 
-// Cross-attention of one query row over the chunk's S cached encoder keys / values (bf16 [B*S][2d]: K at column h*64, V at
+// Cross-attention of one query row over the chunk's S cached encoder keys / values (op16 [B*S][2d]: K at column h*64, V at
 // column d + h*64).  One block per (chunk, head), 256 threads.
-__global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv, int S, int d,
+__global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __restrict__ q, const op16* __restrict__ kv, int S, int d,
                                                              float* __restrict__ out) {
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   extern __shared__ float sm[];                // q[64] | p[S]
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
   float* sp = sm + DH;
   if (tid < DH) sq[tid] = q[static_cast<size_t>(b) * d + h * DH + tid];
   __syncthreads();
-  const __nv_bfloat16* base = kv + static_cast<size_t>(b) * S * 2 * d;
+  const op16* base = kv + static_cast<size_t>(b) * S * 2 * d;
   float lmax = -INFINITY;
   for (int t = tid; t < S; t += blockDim.x) {
     const uint4* k8 = reinterpret_cast<const uint4*>(base + static_cast<size_t>(t) * 2 * d + h * DH);
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        s = fmaf(__uint_as_float(w[j] << 16), sq[8 * i + 2 * j], s);
-        s = fmaf(__uint_as_float(w[j] & 0xffff0000u), sq[8 * i + 2 * j + 1], s);
+        s = fmaf(unpack_op16_lo(w[j]), sq[8 * i + 2 * j], s);
+        s = fmaf(unpack_op16_hi(w[j]), sq[8 * i + 2 * j + 1], s);
       }
     }
     s *= 0.125f;
@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
   for (int t = warp; t < S; t += 8) {
     const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(base + static_cast<size_t>(t) * 2 * d + d + h * DH) + lane);
     const float p = sp[t];
-    a0 = fmaf(p, __uint_as_float(u << 16), a0);
-    a1 = fmaf(p, __uint_as_float(u & 0xffff0000u), a1);
+    a0 = fmaf(p, unpack_op16_lo(u), a0);
+    a1 = fmaf(p, unpack_op16_hi(u), a1);
   }
   __shared__ float part[8][DH];
   part[warp][2 * lane] = a0;
@@ -382,26 +382,26 @@ int forward_one(Replica* m, int B, int S, int T, bool want_logits, int suppress_
   for (int l = 0; l < w.n_layers; ++l) {
     const DecLayerW& lw = w.layers[l];
     // self-attention over the cache
-    if ((rc = launch_layernorm(s.x.p, lw.ln1_g, lw.ln1_b, B, d, nullptr, s.xn.p, st)) != WB_OK) return rc;
+    if ((rc = launch_layernorm(s.x.p, lw.ln1_g, lw.ln1_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
     if ((rc = launch_dec_linear<0>(s.xn.p, B, d, lw.sa_wqkv, lw.sa_bqkv, 3 * d, s.qkv.p, 3 * d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     float* cache = s.kv_self.p + static_cast<size_t>(l) * B * T * 2 * d;
     dec_self_attn_kernel<<<dim3(B, H), 128, (DH + T) * sizeof(float), st>>>(s.qkv.p, cache, T, d, s.pos.p, s.att.p);
     count_launch();
     if ((rc = launch_dec_linear<2>(s.att.p, B, d, lw.sa_wo, lw.sa_bo, d, s.x.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     // cross-attention over the precomputed encoder K/V
-    if ((rc = launch_layernorm(s.x.p, lw.ln2_g, lw.ln2_b, B, d, nullptr, s.xn.p, st)) != WB_OK) return rc;
+    if ((rc = launch_layernorm(s.x.p, lw.ln2_g, lw.ln2_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
     if ((rc = launch_dec_linear<0>(s.xn.p, B, d, lw.ca_wq, lw.ca_bq, d, s.q.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
-    const bf16* kv = s.kv_cross.p + static_cast<size_t>(l) * B * S * 2 * d;
+    const op16* kv = s.kv_cross.p + static_cast<size_t>(l) * B * S * 2 * d;
     dec_cross_attn_kernel<<<dim3(B, H), 256, (DH + S) * sizeof(float), st>>>(s.q.p, kv, S, d, s.att.p);
     count_launch();
     if ((rc = launch_dec_linear<2>(s.att.p, B, d, lw.ca_wo, lw.ca_bo, d, s.x.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     // FFN
-    if ((rc = launch_layernorm(s.x.p, lw.ln3_g, lw.ln3_b, B, d, nullptr, s.xn.p, st)) != WB_OK) return rc;
+    if ((rc = launch_layernorm(s.x.p, lw.ln3_g, lw.ln3_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
     if ((rc = launch_dec_linear<1>(s.xn.p, B, d, lw.w1, lw.b1, 4 * d, s.hid.p, 4 * d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     if ((rc = launch_dec_linear<2>(s.hid.p, B, 4 * d, lw.w2, lw.b2, d, s.x.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
   }
   if (want_logits) {
-    if ((rc = launch_layernorm(s.x.p, w.ln_g, w.ln_b, B, d, nullptr, s.xn.p, st)) != WB_OK) return rc;
+    if ((rc = launch_layernorm(s.x.p, w.ln_g, w.ln_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
     if ((rc = launch_dec_linear<3>(s.xn.p, B, d, w.tok_emb, nullptr, w.n_vocab, logits_out, w.n_vocab, w.suppress[suppress_set], s.part_val.p,
                                    s.part_idx.p, &s.argmax_blocks, st)) != WB_OK)
       return rc;
@@ -434,7 +434,7 @@ int load_decoder(Replica* m, const AprFile& f, Uploader& up) {
   if ((rc = f32_param(up.present("decoder.embed_tokens.weight") ? "decoder.embed_tokens.weight" : "decoder.token_embedding", V * d, 0.f, &w.tok_emb)) != WB_OK) return rc;
   if ((rc = f32_param(up.present("decoder.embed_positions.weight") ? "decoder.embed_positions.weight" : "decoder.positional_embedding", C * d, 0.f, &w.pos_emb)) != WB_OK) return rc;
   w.layers.resize(L);
-  DevBuf<float> tmp;                                          // f32 staging of [k_proj; v_proj] before the bf16 conversion
+  DevBuf<float> tmp;                                          // f32 staging of [k_proj; v_proj] before the op16 conversion
   if ((rc = tmp.ensure(2 * d * d)) != WB_OK) return rc;
   for (size_t i = 0; i < L; ++i) {
     DecLayerW& lw = w.layers[i];
@@ -459,7 +459,7 @@ int load_decoder(Replica* m, const AprFile& f, Uploader& up) {
     if ((rc = launch_fill_f32(tmp.p, 2 * d * d, 0.f, st)) != WB_OK) return rc;
     if ((rc = up.load_f32(p + ".encoder_attn.k_proj.weight", tmp.p, d * d)) || (rc = up.load_f32(p + ".encoder_attn.v_proj.weight", tmp.p + d * d, d * d))) return rc;
     if ((rc = dev_alloc(m, 2 * d * d, &lw.ca_wkv)) != WB_OK) return rc;
-    if ((rc = launch_f32_to_bf16(tmp.p, lw.ca_wkv, 2 * d * d, st)) != WB_OK) return rc;
+    if ((rc = launch_f32_to_op16(tmp.p, lw.ca_wkv, 2 * d * d, st)) != WB_OK) return rc;
     if ((rc = dev_alloc(m, 2 * d, &lw.ca_bkv)) || (rc = launch_fill_f32(lw.ca_bkv, 2 * d, 0.f, st))) return rc;
     if ((rc = up.load_f32(p + ".encoder_attn.k_proj.bias", lw.ca_bkv, d)) || (rc = up.load_f32(p + ".encoder_attn.v_proj.bias", lw.ca_bkv + d, d))) return rc;
     // FFN
@@ -491,9 +491,9 @@ void free_decode_state(Replica* m) {
   m->dstate = nullptr;
 }
 
-// K/V of the cross-attention for every decoder layer: [k_proj; v_proj] (2d x d, bf16) applied to the B*S encoder rows by the
-// tcgen05 GEMM, bias in the epilogue, bf16 out [B*S][2d].  d_states: bf16 [B*S][d] on this device.
-static int cross_kv(Replica* m, const bf16* d_states, int B, int S) {
+// K/V of the cross-attention for every decoder layer: [k_proj; v_proj] (2d x d, op16) applied to the B*S encoder rows by the
+// tcgen05 GEMM, bias in the epilogue, op16 out [B*S][2d].  d_states: op16 [B*S][d] on this device.
+static int cross_kv(Replica* m, const op16* d_states, int B, int S) {
   DecodeState& s = *m->dstate;
   const DecoderW& w = m->dec;
   const int d = w.d;
@@ -511,16 +511,16 @@ static int cross_kv(Replica* m, const bf16* d_states, int B, int S) {
   return WB_OK;
 }
 
-int decoder_cross_kv(Replica* m, const bf16* d_states, int B) {
+int decoder_cross_kv(Replica* m, const op16* d_states, int B) {
   if (!m->dec.loaded) return set_error(WB_ERR_MODEL, "the .apr file carries no decoder tensors");
   int rc = ensure_decode_state(m, B, N_POS_30S, std::max(m->dstate ? m->dstate->cap_T : 0, 8));
   if (rc != WB_OK) return rc;
   return cross_kv(m, d_states, B, N_POS_30S);
 }
 
-// WhisperApr::decode with GreedyDecoder for B chunks side by side.  d_states: bf16 [B][S][d] on this device.  tokens_out
+// WhisperApr::decode with GreedyDecoder for B chunks side by side.  d_states: op16 [B][S][d] on this device.  tokens_out
 // [B][max_tokens] (host, padded with EOT), lens_out [B].  The caller holds the replica lock and has set the device.
-int decoder_greedy_s(Replica* m, const bf16* d_states, int B, int S, const int* initial_tokens, int n_init, int max_tokens,
+int decoder_greedy_s(Replica* m, const op16* d_states, int B, int S, const int* initial_tokens, int n_init, int max_tokens,
                      int suppress_timestamps, int* tokens_out, int* lens_out, float* logits_last_host) {
   if (!m->dec.loaded) return set_error(WB_ERR_MODEL, "the .apr file carries no decoder tensors");
   const DecoderW& w = m->dec;
@@ -576,26 +576,26 @@ int decoder_greedy_s(Replica* m, const bf16* d_states, int B, int S, const int* 
 }
 
 // test hook: K and V of one decoder layer's cross-attention for one chunk of S rows, as f32 [S][d] each
-int decoder_debug_cross_kv(Replica* m, const bf16* d_states, int S, int layer, float* k_out, float* v_out) {
+int decoder_debug_cross_kv(Replica* m, const op16* d_states, int S, int layer, float* k_out, float* v_out) {
   if (!m->dec.loaded) return set_error(WB_ERR_MODEL, "the .apr file carries no decoder tensors");
   if (layer < 0 || layer >= m->dec.n_layers) return set_error(WB_ERR_MODEL, "decoder layer out of range");
   int rc = ensure_decode_state(m, 1, S, 8);
   if (rc != WB_OK) return rc;
   if ((rc = cross_kv(m, d_states, 1, S)) != WB_OK) return rc;
   const int d = m->dec.d;
-  std::vector<bf16> h(static_cast<size_t>(S) * 2 * d);
+  std::vector<op16> h(static_cast<size_t>(S) * 2 * d);
   WB_CUDA_OK(cudaMemcpyAsync(h.data(), m->dstate->kv_cross.p + static_cast<size_t>(layer) * S * 2 * d, h.size() * 2, cudaMemcpyDeviceToHost, m->stream));
   cudaError_t e = cudaStreamSynchronize(m->stream);
   if (e != cudaSuccess) return set_error(WB_ERR_CUDA, std::string("cross K/V GEMM failed: ") + cudaGetErrorString(e));
   for (int t = 0; t < S; ++t)
     for (int i = 0; i < d; ++i) {
-      k_out[static_cast<size_t>(t) * d + i] = __bfloat162float(h[static_cast<size_t>(t) * 2 * d + i]);
-      v_out[static_cast<size_t>(t) * d + i] = __bfloat162float(h[static_cast<size_t>(t) * 2 * d + d + i]);
+      k_out[static_cast<size_t>(t) * d + i] = op16_to_float(h[static_cast<size_t>(t) * 2 * d + i]);
+      v_out[static_cast<size_t>(t) * d + i] = op16_to_float(h[static_cast<size_t>(t) * 2 * d + d + i]);
     }
   return WB_OK;
 }
 
-int decoder_greedy(Replica* m, const bf16* d_states, int B, const int* initial_tokens, int n_init, int max_tokens, int suppress_timestamps,
+int decoder_greedy(Replica* m, const op16* d_states, int B, const int* initial_tokens, int n_init, int max_tokens, int suppress_timestamps,
                    int* tokens_out, int* lens_out) {
   return decoder_greedy_s(m, d_states, B, N_POS_30S, initial_tokens, n_init, max_tokens, suppress_timestamps, tokens_out, lens_out, nullptr);
 }

@@ -10,22 +10,26 @@ namespace {
 // LayerNorm::forward (src/model/encoder.rs:219-251): per row mean, POPULATION variance (two passes, as the
 // reference), 1/sqrt(var + 1e-5), * gamma + beta.  One warp per row; the row lives in registers between the
 // passes so x is read from HBM once (4 B/elem in, 2 B/elem out for the bf16 GEMM operand).
-template <int NV>   // float4 per lane; d == 128 * nv, nv <= NV
+template <int NP>   // pairs of float4 (8 consecutive elements) per lane; d == 8 * n_pairs, n_pairs <= 32 * NP
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d,
-                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+                 uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const int nv = d >> 7;
+  const int n_pairs = d >> 3;
+  // a lane owns 8 consecutive elements per step: 32 B loads, and a 16 B bf16 store -- the widest a lane can issue, which is what
+  // keeps the store stream efficient when `out` is a PEER device's memory (the gather writes the final states over NVLink)
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
-  float4 v[NV];
+  float4 v[NP][2];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (i < nv) {
-      v[i] = xr[lane + 32 * i];
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int i = 0; i < NP; ++i) {
+    const int p = lane + 32 * i;
+    if (p < n_pairs) {
+      v[i][0] = xr[2 * p];
+      v[i][1] = xr[2 * p + 1];
+      sum += ((v[i][0].x + v[i][0].y) + (v[i][0].z + v[i][0].w)) + ((v[i][1].x + v[i][1].y) + (v[i][1].z + v[i][1].w));
     }
   }
 #pragma unroll
@@ -33,10 +37,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   const float mean = sum / static_cast<float>(d);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (i < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-      sq += (a * a + b * b) + (c * c + e * e);
+  for (int i = 0; i < NP; ++i) {
+    if (lane + 32 * i < n_pairs) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float a = v[i][h].x - mean, b = v[i][h].y - mean, c = v[i][h].z - mean, e = v[i][h].w - mean;
+        sq += (a * a + b * b) + (c * c + e * e);
+      }
     }
   }
 #pragma unroll
@@ -45,21 +52,38 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (i < nv) {
-      const float4 g = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
-      float4 r;
-      r.x = (v[i].x - mean) * inv * g.x + bb.x;
-      r.y = (v[i].y - mean) * inv * g.y + bb.y;
-      r.z = (v[i].z - mean) * inv * g.z + bb.z;
-      r.w = (v[i].w - mean) * inv * g.w + bb.w;
-      if (out_bf16) {
-        uint2 w;
-        w.x = pack_bf16x2(r.x, r.y);
-        w.y = pack_bf16x2(r.z, r.w);
-        reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * d)[lane + 32 * i] = w;
+  for (int i = 0; i < NP; ++i) {
+    const int p = lane + 32 * i;
+    if (p < n_pairs) {
+      float4 r[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 g = __ldg(g4 + 2 * p + h), bb = __ldg(b4 + 2 * p + h);
+        r[h].x = (v[i][h].x - mean) * inv * g.x + bb.x;
+        r[h].y = (v[i][h].y - mean) * inv * g.y + bb.y;
+        r[h].z = (v[i][h].z - mean) * inv * g.z + bb.z;
+        r[h].w = (v[i][h].w - mean) * inv * g.w + bb.w;
       }
-      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * d)[lane + 32 * i] = r;
+      if (out_16) {
+        uint4 w;
+        if (as_bf16) {             // the caller asked for bf16 states (WB_BF16): a user-facing format, not the operand format
+          w.x = pack_bf16x2(r[0].x, r[0].y);
+          w.y = pack_bf16x2(r[0].z, r[0].w);
+          w.z = pack_bf16x2(r[1].x, r[1].y);
+          w.w = pack_bf16x2(r[1].z, r[1].w);
+        } else {
+          w.x = pack_op16x2(r[0].x, r[0].y);
+          w.y = pack_op16x2(r[0].z, r[0].w);
+          w.z = pack_op16x2(r[1].x, r[1].y);
+          w.w = pack_op16x2(r[1].z, r[1].w);
+        }
+        reinterpret_cast<uint4*>(out_16 + static_cast<long long>(row) * d)[p] = w;
+      }
+      if (out_f32) {
+        float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * d);
+        o[2 * p] = r[0];
+        o[2 * p + 1] = r[1];
+      }
     }
   }
 }
@@ -67,7 +91,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // Any d: one warp per row, three passes over global/L1.
 __global__ void __launch_bounds__(256)
 layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows,
-                         int d, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+                         int d, uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -84,38 +108,40 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
   const float inv = 1.0f / sqrtf(sq / static_cast<float>(d) + 1e-5f);
   for (int i = lane; i < d; i += 32) {
     const float r = (xr[i] - mean) * inv * gamma[i] + beta[i];
-    if (out_bf16) out_bf16[static_cast<long long>(row) * d + i] = __float2bfloat16_rn(r);
+    if (out_16) {
+      if (as_bf16) reinterpret_cast<__nv_bfloat16*>(out_16)[static_cast<long long>(row) * d + i] = __float2bfloat16_rn(r);
+      else reinterpret_cast<op16*>(out_16)[static_cast<long long>(row) * d + i] = float_to_op16(r);
+    }
     if (out_f32) out_f32[static_cast<long long>(row) * d + i] = r;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, op16* __restrict__ out, size_t n) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+  for (; i < n; i += stride) out[i] = float_to_op16(in[i]);
 }
 // int8 payload (format/mod.rs:632-672) -> bf16 integer value (exact: |q| <= 127); the per-tensor scale is applied in
 // the GEMM epilogue.
-__global__ void i8_to_bf16_kernel(const int8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+__global__ void i8_to_bf16_kernel(const int8_t* __restrict__ in, op16* __restrict__ out, size_t n) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(static_cast<float>(in[i]));
+  for (; i < n; i += stride) out[i] = float_to_op16(static_cast<float>(in[i]));
 }
 // packed int4, even index -> low nibble, two's complement (model/quantized.rs:1887-1969)
 __device__ __forceinline__ int unpack_i4(uint8_t byte, size_t idx) {
   int nib = (idx & 1) ? (byte >> 4) : (byte & 0x0F);
   return nib >= 8 ? nib - 16 : nib;
 }
-__global__ void i4_to_bf16_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+__global__ void i4_to_bf16_kernel(const uint8_t* __restrict__ in, op16* __restrict__ out, size_t n) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(static_cast<float>(unpack_i4(in[i >> 1], i)));
+  for (; i < n; i += stride) out[i] = float_to_op16(static_cast<float>(unpack_i4(in[i >> 1], i)));
 }
 // Vector forms used by the per-layer weight expansion (n % 32 == 0, 16-byte aligned): 16 B of packed payload per thread.
-__device__ __forceinline__ uint32_t bf16x2_from_ints(int lo, int hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(static_cast<float>(lo), static_cast<float>(hi));
-  return *reinterpret_cast<uint32_t*>(&v);
+__device__ __forceinline__ uint32_t bf16x2_from_ints(int lo, int hi) {          // exact in either operand format (|q| <= 128)
+  return pack_op16x2(static_cast<float>(lo), static_cast<float>(hi));
 }
 __global__ void __launch_bounds__(256) i8_to_bf16_vec_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n16) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -164,7 +190,7 @@ __global__ void i4_to_f32_kernel(const uint8_t* __restrict__ in, float scale, fl
 }
 // Conv1d weight [out][in][3] (encoder.rs:96-98) -> [out][3][in]: row `out` becomes the K-major GEMM operand whose
 // K index is tap*in + channel, matching the contiguous 3-frame window of the activation view.
-__global__ void conv_repack_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int c_out, int c_in) {
+__global__ void conv_repack_kernel(const op16* __restrict__ in, op16* __restrict__ out, int c_out, int c_in) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t n = static_cast<size_t>(c_out) * c_in * 3;
   if (i >= n) return;
@@ -174,7 +200,7 @@ __global__ void conv_repack_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
   out[i] = in[(static_cast<size_t>(o) * c_in + ch) * 3 + tap];
 }
 // mel f32 [B][T][m] -> bf16 [B][T+2][m], guard rows 0 and T+1 zero
-__global__ void mel_pad_bf16_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int T, int m) {
+__global__ void mel_pad_bf16_kernel(const float* __restrict__ mel, op16* __restrict__ out, int T, int m) {
   const int b = blockIdx.y;
   const long long per = static_cast<long long>(T + 2) * m;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -182,11 +208,11 @@ __global__ void mel_pad_bf16_kernel(const float* __restrict__ mel, __nv_bfloat16
   const long long row = i / m;
   float v = 0.f;
   if (row >= 1 && row <= T) v = mel[static_cast<long long>(b) * T * m + (i - m)];
-  out[b * per + i] = __float2bfloat16_rn(v);
+  out[b * per + i] = float_to_op16(v);
 }
-__global__ void fill_zero_rows_kernel(__nv_bfloat16* base, long long batch_stride, int row_elems) {
-  __nv_bfloat16* p = base + static_cast<long long>(blockIdx.y) * batch_stride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_elems; i += gridDim.x * blockDim.x) p[i] = __float2bfloat16_rn(0.f);
+__global__ void fill_zero_rows_kernel(op16* base, long long batch_stride, int row_elems) {
+  op16* p = base + static_cast<long long>(blockIdx.y) * batch_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_elems; i += gridDim.x * blockDim.x) p[i] = float_to_op16(0.f);
 }
 
 inline unsigned grid_for(size_t n) {
@@ -196,32 +222,33 @@ inline unsigned grid_for(size_t n) {
 
 }  // namespace
 
-int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16, float* out_f32,
-                     cudaStream_t stream) {
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, void* out_16v, bool out_16_is_bf16,
+                     float* out_f32, cudaStream_t stream) {
+  uint16_t* out_bf16 = static_cast<uint16_t*>(out_16v);
   if (rows <= 0) return WB_OK;
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
   if (d % 128 == 0 && d <= 2048) {
-    if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_f32);
-    else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_f32);
-    else layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_f32);
+    if (d <= 512) layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
+    else if (d <= 1280) layernorm_kernel<5><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
+    else layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
     count_launch();
   } else {
-    layernorm_generic_kernel<<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_f32);
+    layernorm_generic_kernel<<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
     count_launch();
   }
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
 
-int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
+int launch_f32_to_op16(const float* in, op16* out, size_t n, cudaStream_t s) {
   if (n == 0) return WB_OK;
   f32_to_bf16_kernel<<<grid_for(n), 256, 0, s>>>(in, out, n);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
-int launch_i8_to_bf16(const int8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
+int launch_i8_to_op16(const int8_t* in, op16* out, size_t n, cudaStream_t s) {
   if (n == 0) return WB_OK;
   if (n % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     i8_to_bf16_vec_kernel<<<grid_for(n / 16), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n / 16);
@@ -234,7 +261,7 @@ int launch_i8_to_bf16(const int8_t* in, __nv_bfloat16* out, size_t n, cudaStream
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
-int launch_i4_to_bf16(const uint8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
+int launch_i4_to_op16(const uint8_t* in, op16* out, size_t n, cudaStream_t s) {
   if (n == 0) return WB_OK;
   if (n % 32 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     i4_to_bf16_vec_kernel<<<grid_for(n / 32), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n / 32);
@@ -261,14 +288,14 @@ int launch_i4_to_f32(const uint8_t* in, float scale, float* out, size_t n, cudaS
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
-int launch_conv_repack(const __nv_bfloat16* in, __nv_bfloat16* out, int c_out, int c_in, cudaStream_t s) {
+int launch_conv_repack(const op16* in, op16* out, int c_out, int c_in, cudaStream_t s) {
   const size_t n = static_cast<size_t>(c_out) * c_in * 3;
   conv_repack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(in, out, c_out, c_in);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
-int launch_mel_pad_bf16(const float* mel, __nv_bfloat16* out, int B, int T, int m, cudaStream_t s) {
+int launch_mel_pad_op16(const float* mel, op16* out, int B, int T, int m, cudaStream_t s) {
   if (B <= 0) return WB_OK;
   const long long per = static_cast<long long>(T + 2) * m;
   dim3 grid(static_cast<unsigned>((per + 255) / 256), B);
@@ -277,7 +304,7 @@ int launch_mel_pad_bf16(const float* mel, __nv_bfloat16* out, int B, int T, int 
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
-int launch_fill_bf16_rows(__nv_bfloat16* base, long long batch_stride, int B, int row_elems, cudaStream_t s) {
+int launch_fill_op16_rows(op16* base, long long batch_stride, int B, int row_elems, cudaStream_t s) {
   if (B <= 0 || row_elems <= 0) return WB_OK;
   dim3 grid((row_elems + 255) / 256, B);
   fill_zero_rows_kernel<<<grid, 256, 0, s>>>(base, batch_stride, row_elems);

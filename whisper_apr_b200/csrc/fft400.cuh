@@ -100,4 +100,17 @@ WB_HD float rfft_power(cf zk, cf zm, cf w) {
   return re * re + im * im;
 }
 
+// Powers of the partner bins k and 200-k (0 < k < 200, k != 100) in one go.  zk = Z[k] / 2, zm = Z[200-k] / 2 (the packed transform
+// already halved: the 1/2 of the even/odd split is folded into the W200 twiddle table), w = exp(-2*pi*i*k/400):
+//   E = zk + conj zm,  T = w * (-i) * (zk - conj zm);   X[k] = E + T,   X[200-k] = conj(E - T)
+// -- half the arithmetic of two rfft_power calls, which recompute E and T for each partner.
+WB_HD void rfft_power_pair(cf zk, cf zm, cf w, float& pk, float& pm) {
+  const float ex = zk.x + zm.x, ey = zk.y - zm.y;
+  const float dx = zk.x - zm.x, dy = zk.y + zm.y;
+  const float tx = w.x * dy + w.y * dx, ty = w.y * dy - w.x * dx;
+  const float ax = ex + tx, ay = ey + ty, bx = ex - tx, by = ey - ty;
+  pk = ax * ax + ay * ay;
+  pm = bx * bx + by * by;
+}
+
 }  // namespace wb

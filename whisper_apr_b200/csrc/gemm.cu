@@ -86,14 +86,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
     for (int i = 0; i < 32; ++i) acc[i] = gelu_fast(acc[i]);
   }
   if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n0);
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<op16*>(p.out) + out_row * p.ldc + n0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint4 w;
-      w.x = pack_bf16x2(acc[8 * i + 0], acc[8 * i + 1]);
-      w.y = pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]);
-      w.z = pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]);
-      w.w = pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]);
+      w.x = pack_op16x2(acc[8 * i + 0], acc[8 * i + 1]);
+      w.y = pack_op16x2(acc[8 * i + 2], acc[8 * i + 3]);
+      w.z = pack_op16x2(acc[8 * i + 4], acc[8 * i + 5]);
+      w.w = pack_op16x2(acc[8 * i + 6], acc[8 * i + 7]);
       o4[i] = w;
     }
   } else {
@@ -315,8 +315,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int k = 0; k < 8; ++k) a[k] = gelu_tanh_approx(a[k]);
           }
           const uint32_t j = static_cast<uint32_t>(half * 4 + i);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pack_bf16x2(a[0], a[1])),
-                       "r"(pack_bf16x2(a[2], a[3])), "r"(pack_bf16x2(a[4], a[5])), "r"(pack_bf16x2(a[6], a[7]))
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pack_op16x2(a[0], a[1])),
+                       "r"(pack_op16x2(a[2], a[3])), "r"(pack_op16x2(a[4], a[5])), "r"(pack_op16x2(a[6], a[7]))
                        : "memory");
         }
       };
@@ -425,7 +425,7 @@ int gemm_init() {
   return WB_OK;
 }
 
-int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
   int rc = gemm_init();
   if (rc != WB_OK) return rc;
@@ -433,7 +433,7 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode.load(std::memory_order_acquire)(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode.load(std::memory_order_acquire)(out, kOp16IsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -467,10 +467,10 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   const int BN = (g.N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   uint64_t batch_stride = g.n_batch > 1 ? static_cast<uint64_t>(g.a_batch_stride) * 2 : static_cast<uint64_t>(g.a_row_stride) * 2;
-  rc = make_tmap_bf16_3d(&ta, g.A, g.K, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.a_row_stride) * 2, batch_stride,
+  rc = make_tmap_op16_3d(&ta, g.A, g.K, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.a_row_stride) * 2, batch_stride,
                          BK, BM);
   if (rc != WB_OK) return rc;
-  rc = make_tmap_bf16_3d(&tb, g.W, g.K, g.N, 1, static_cast<uint64_t>(g.K) * 2, static_cast<uint64_t>(g.K) * 2 * g.N, BK, BN / 2);
+  rc = make_tmap_op16_3d(&tb, g.W, g.K, g.N, 1, static_cast<uint64_t>(g.K) * 2, static_cast<uint64_t>(g.K) * 2 * g.N, BK, BN / 2);
   if (rc != WB_OK) return rc;
   GemmKParams kp;
   kp.rows_per_batch = g.rows_per_batch;
@@ -487,12 +487,12 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.bias = g.bias;
   kp.out = g.out;
   kp.pe = g.pe;
-  kp.idesc = umma_idesc_bf16(2 * BM, BN, 0);
+  kp.idesc = umma_idesc_op16(2 * BM, BN, 0);
   const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
   CUtensorMap tc = ta;                                    // the f32 debug / positional-embedding epilogues do not read it
   if (g.epilogue == EPI_BF16 || g.epilogue == EPI_GELU_BF16) {
-    __nv_bfloat16* base = static_cast<__nv_bfloat16*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
-    rc = make_tmap_bf16_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 2,
+    op16* base = static_cast<op16*>(g.out) + static_cast<long long>(g.out_row_off) * g.ldc;
+    rc = make_tmap_op16_3d(&tc, base, g.N, g.rows_per_batch, g.n_batch, static_cast<uint64_t>(g.ldc) * 2,
                            g.n_batch > 1 ? static_cast<uint64_t>(g.out_rows_per_batch) * g.ldc * 2 : static_cast<uint64_t>(g.ldc) * 2 * g.rows_per_batch,
                            64, 32);
     if (rc != WB_OK) return rc;

@@ -33,31 +33,31 @@ __global__ void copy_f32_unaligned_kernel(const uint8_t* __restrict__ src, float
     }
   }
 }
-__global__ void f32_unaligned_to_bf16_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+__global__ void f32_unaligned_to_bf16_kernel(const uint8_t* __restrict__ src, op16* __restrict__ dst, size_t n) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) {
     const uint8_t* p = src + 4 * i;
     const uint32_t u = p[0] | (p[1] << 8) | (p[2] << 16) | (static_cast<uint32_t>(p[3]) << 24);
-    dst[i] = __float2bfloat16_rn(__uint_as_float(u));
+    dst[i] = float_to_op16(__uint_as_float(u));
   }
 }
-// per-channel symmetric int8 of a bf16 weight matrix [rows][cols] (quantize_f32_to_i8_per_channel, model/quantized.rs:1769-1794 over
+// per-channel symmetric int8 of a op16 weight matrix [rows][cols] (quantize_f32_to_i8_per_channel, model/quantized.rs:1769-1794 over
 // quantize_f32_to_i8 :1732-1756): scale = absmax / 127 (1.0 when absmax < 1e-10), q = clamp(round(x / scale), -128, 127).
 // One warp per row.
-__global__ void __launch_bounds__(256) quant_i8_rows_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, int8_t* __restrict__ q,
+__global__ void __launch_bounds__(256) quant_i8_rows_kernel(const op16* __restrict__ w, int rows, int cols, int8_t* __restrict__ q,
                                                             float* __restrict__ scales) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const __nv_bfloat16* wr = w + static_cast<size_t>(row) * cols;
+  const op16* wr = w + static_cast<size_t>(row) * cols;
   float mx = 0.f;
-  for (int i = lane; i < cols; i += 32) mx = fmaxf(mx, fabsf(__bfloat162float(wr[i])));
+  for (int i = lane; i < cols; i += 32) mx = fmaxf(mx, fabsf(op16_to_float(wr[i])));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   const float scale = mx < 1e-10f ? 1.0f : mx / 127.0f;
   for (int i = lane; i < cols; i += 32) {
-    const float v = roundf(__bfloat162float(wr[i]) / scale);          // f32::round: half away from zero, as roundf
+    const float v = roundf(op16_to_float(wr[i]) / scale);          // f32::round: half away from zero, as roundf
     q[static_cast<size_t>(row) * cols + i] = static_cast<int8_t>(fminf(fmaxf(v, -128.f), 127.f));
   }
   if (lane == 0) scales[row] = scale;
@@ -77,9 +77,9 @@ int launch_copy_f32_bytes(const uint8_t* src, float* dst, size_t n, cudaStream_t
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }
-int launch_f32_bytes_to_bf16(const uint8_t* src, bf16* dst, size_t n, cudaStream_t s) {
+int launch_f32_bytes_to_op16(const uint8_t* src, op16* dst, size_t n, cudaStream_t s) {
   if (n == 0) return WB_OK;
-  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) return launch_f32_to_bf16(reinterpret_cast<const float*>(src), dst, n, s);
+  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) return launch_f32_to_op16(reinterpret_cast<const float*>(src), dst, n, s);
   f32_unaligned_to_bf16_kernel<<<grid_for(n), 256, 0, s>>>(src, dst, n);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
@@ -103,10 +103,10 @@ int new_f32_param(Replica* m, Uploader& up, const std::string& name, size_t coun
   return up.load_f32(name, *out, count);
 }
 
-int new_weight(Replica* m, Uploader& up, const std::string& name, size_t count, bf16** out, float* scale) {
+int new_weight(Replica* m, Uploader& up, const std::string& name, size_t count, op16** out, float* scale) {
   int rc = dev_alloc(m, count, out);
   if (rc != WB_OK) return rc;
-  WB_CUDA_OK(cudaMemsetAsync(*out, 0, count * sizeof(bf16), m->stream));
+  WB_CUDA_OK(cudaMemsetAsync(*out, 0, count * sizeof(op16), m->stream));
   return up.load_bf16(name, *out, count, scale);
 }
 
@@ -131,12 +131,12 @@ int load_encoder(Replica* m, const AprFile& f, Uploader& up) {
   const bool quant = f.cfg.quantization == 2 || f.cfg.quantization == 3;
   cudaStream_t st = m->stream;
 
-  // conv stem: [out][in][3] -> bf16 -> [out][3][in]
+  // conv stem: [out][in][3] -> op16 -> [out][3][in]
   {
-    DevBuf<bf16> t1, t2;
+    DevBuf<op16> t1, t2;
     if ((rc = t1.ensure(d * nm * 3)) != WB_OK || (rc = t2.ensure(d * d * 3)) != WB_OK) return rc;
-    WB_CUDA_OK(cudaMemsetAsync(t1.p, 0, d * nm * 3 * sizeof(bf16), st));
-    WB_CUDA_OK(cudaMemsetAsync(t2.p, 0, d * d * 3 * sizeof(bf16), st));
+    WB_CUDA_OK(cudaMemsetAsync(t1.p, 0, d * nm * 3 * sizeof(op16), st));
+    WB_CUDA_OK(cudaMemsetAsync(t2.p, 0, d * d * 3 * sizeof(op16), st));
     if ((rc = up.load_bf16("encoder.conv1.weight", t1.p, d * nm * 3, &m->conv1_s)) != WB_OK) return rc;
     if ((rc = dev_alloc(m, d * nm * 3, &m->conv1_w)) != WB_OK) return rc;
     if ((rc = launch_conv_repack(t1.p, m->conv1_w, static_cast<int>(d), static_cast<int>(nm), st)) != WB_OK) return rc;
@@ -181,7 +181,7 @@ int load_encoder(Replica* m, const AprFile& f, Uploader& up) {
     if ((rc = launch_fill_f32(w.bqkv, 3 * d, 0.f, st)) != WB_OK) return rc;
     float sc[3] = {1.f, 1.f, 1.f};
     if (quant) {
-      // the packed bytes stay as they are in HBM; every layer shares one set of bf16 expansion buffers
+      // the packed bytes stay as they are in HBM; every layer shares one set of op16 expansion buffers
       const size_t qb = f.cfg.quantization == 2 ? d * d : d * d / 2;        // bytes of one d x d tensor (d is even)
       if ((rc = dev_alloc(m, 3 * qb, &w.pqkv)) != WB_OK || (rc = dev_alloc(m, qb, &w.po)) != WB_OK ||
           (rc = dev_alloc(m, 4 * qb, &w.p1)) != WB_OK || (rc = dev_alloc(m, 4 * qb, &w.p2)) != WB_OK)
@@ -200,7 +200,7 @@ int load_encoder(Replica* m, const AprFile& f, Uploader& up) {
       if ((rc = up.load_packed(p + ".fc2.weight", w.p2, 4 * d * d, &w.s2)) != WB_OK) return rc;
     } else {
       if ((rc = dev_alloc(m, 3 * d * d, &w.wqkv)) != WB_OK) return rc;
-      WB_CUDA_OK(cudaMemsetAsync(w.wqkv, 0, 3 * d * d * sizeof(bf16), st));
+      WB_CUDA_OK(cudaMemsetAsync(w.wqkv, 0, 3 * d * d * sizeof(op16), st));
       for (int k = 0; k < 3; ++k) {
         if ((rc = up.load_bf16(p + proj[k] + ".weight", w.wqkv + k * d * d, d * d, &sc[k])) != WB_OK) return rc;
         if ((rc = up.load_f32(p + proj[k] + ".bias", w.bqkv + k * d, d)) != WB_OK) return rc;
@@ -303,8 +303,8 @@ int load_replica(Replica* m, const AprFile& f, const uint8_t* /*pinned_base*/) {
   return WB_OK;
 }
 
-// On-device requantisation of resident bf16 weights to per-channel int8 (model/quantized.rs:1769-1813): one scale per output row
-// of every linear weight; the packed int8 rows replace the bf16 matrices in HBM and are expanded per layer like `.apr` int8 payloads,
+// On-device requantisation of resident op16 weights to per-channel int8 (model/quantized.rs:1769-1813): one scale per output row
+// of every linear weight; the packed int8 rows replace the op16 matrices in HBM and are expanded per layer like `.apr` int8 payloads,
 // the per-row scale is applied per output column in the GEMM epilogue.
 int requantize_int8_per_channel(Replica* m) {
   if (m->quant != 0) return set_error(WB_ERR_MODEL, "per-channel requantisation needs a model loaded from f32 payloads");
@@ -316,7 +316,7 @@ int requantize_int8_per_channel(Replica* m) {
       (rc = dev_alloc(m, 4 * d * d, &m->xp_1)) != WB_OK || (rc = dev_alloc(m, 4 * d * d, &m->xp_2)) != WB_OK)
     return rc;
   std::vector<void*> old;
-  auto quant_rows = [&](const bf16* w, int rows, int cols, uint8_t** q, float** scales) -> int {
+  auto quant_rows = [&](const op16* w, int rows, int cols, uint8_t** q, float** scales) -> int {
     int r;
     if ((r = dev_alloc(m, static_cast<size_t>(rows) * cols, q)) != WB_OK || (r = dev_alloc(m, rows, scales)) != WB_OK) return r;
     quant_i8_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, rows, cols, reinterpret_cast<int8_t*>(*q), *scales);
@@ -335,7 +335,7 @@ int requantize_int8_per_channel(Replica* m) {
     w.so = w.s1 = w.s2 = 1.f;
   }
   WB_CUDA_OK(cudaStreamSynchronize(st));
-  for (void* p : old) {                                  // the bf16 matrices are gone from HBM: 2 B -> 1 B per weight
+  for (void* p : old) {                                  // the op16 matrices are gone from HBM: 2 B -> 1 B per weight
     auto it = std::find(m->allocs.begin(), m->allocs.end(), p);
     if (it != m->allocs.end()) m->allocs.erase(it);
     cudaFree(p);

@@ -8,7 +8,7 @@ constexpr size_t PIECE = 64ull << 20;     // H2D granularity of the file image
 
 int launch_fill_f32(float* dst, size_t n, float v, cudaStream_t s);
 int launch_copy_f32_bytes(const uint8_t* src, float* dst, size_t n, cudaStream_t s);          // little-endian f32 bytes, any alignment
-int launch_f32_bytes_to_bf16(const uint8_t* src, bf16* dst, size_t n, cudaStream_t s);
+int launch_f32_bytes_to_op16(const uint8_t* src, op16* dst, size_t n, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------------------------
 struct Uploader {
@@ -107,8 +107,8 @@ struct Uploader {
     WB_CUDA_OK(cudaMemcpyAsync(dst, src, copy_bytes, cudaMemcpyDeviceToDevice, m->stream));
     return WB_OK;
   }
-  // GEMM weight -> bf16 (quantised payloads keep their integer value; *scale_out carries the per-tensor scale).
-  int load_bf16(const std::string& name, bf16* dst, size_t count, float* scale_out) {
+  // GEMM weight -> op16 (quantised payloads keep their integer value; *scale_out carries the per-tensor scale).
+  int load_bf16(const std::string& name, op16* dst, size_t count, float* scale_out) {
     const uint8_t* src;
     size_t n;
     float s;
@@ -116,9 +116,9 @@ struct Uploader {
     int rc = payload(name, count, &src, &n, &s);
     if (rc != WB_OK || n == 0) return rc;
     switch (f->cfg.quantization) {
-      case 2: *scale_out = s; return launch_i8_to_bf16(reinterpret_cast<const int8_t*>(src), dst, n, m->stream);
-      case 3: *scale_out = s; return launch_i4_to_bf16(src, dst, n, m->stream);
-      default: return launch_f32_bytes_to_bf16(src, dst, n, m->stream);
+      case 2: *scale_out = s; return launch_i8_to_op16(reinterpret_cast<const int8_t*>(src), dst, n, m->stream);
+      case 3: *scale_out = s; return launch_i4_to_op16(src, dst, n, m->stream);
+      default: return launch_f32_bytes_to_op16(src, dst, n, m->stream);
     }
   }
 };

@@ -158,7 +158,8 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   }
   __syncwarp();
 
-  // ---- step B: 13 tasks per frame on its 8 lanes, two rounds; the powers stay in registers until every z read is done
+  // ---- step B: 13 tasks per frame on its 8 lanes, two rounds; the powers stay in registers until every z read is done.
+  // z holds Z / 2 (the W200 table is pre-halved), so partner bins k and 200-k share E and T (rfft_power_pair).
   float pw0[16], pw1[16];
   {
     const float2* zf = z + fl * ZS;
@@ -169,25 +170,30 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
       for (int q = 0; q < 8; ++q) { const float2 t = zf[q * 25 + pcol]; a[q] = cmake(t.x, t.y); }
       dft8(a);
       if (pcol == 0) {
-        const float re0 = a[0].x + a[0].y, re200 = a[0].x - a[0].y;
+        const float re0 = 2.0f * (a[0].x + a[0].y), re200 = 2.0f * (a[0].x - a[0].y);
         pw0[0] = re0 * re0;
         pw0[8] = re200 * re200;
 #pragma unroll
-        for (int k2 = 1; k2 < 8; ++k2) {
+        for (int k2 = 1; k2 < 4; ++k2) {                   // bins 25 k2 and 200 - 25 k2
           const float2 w = s.tw400[25 * k2];
-          pw0[k2] = rfft_power(a[k2], a[8 - k2], cmake(w.x, w.y));
-          pw0[8 + k2] = 0.f;
+          rfft_power_pair(a[k2], a[8 - k2], cmake(w.x, w.y), pw0[k2], pw0[8 - k2]);
         }
+        {
+          const float2 w = s.tw400[100];
+          float dummy;
+          rfft_power_pair(a[4], a[4], cmake(w.x, w.y), pw0[4], dummy);
+        }
+#pragma unroll
+        for (int k2 = 1; k2 < 8; ++k2) pw0[8 + k2] = 0.f;
       } else {
         cf c[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) { const float2 t = zf[q * 25 + 25 - pcol]; c[q] = cmake(t.x, t.y); }
         dft8(c);
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) {
-          const float2 w1 = s.tw400[pcol + 25 * k2], w2 = s.tw400[25 - pcol + 25 * k2];
-          pw0[k2] = rfft_power(a[k2], c[7 - k2], cmake(w1.x, w1.y));
-          pw0[8 + k2] = rfft_power(c[k2], a[7 - k2], cmake(w2.x, w2.y));
+        for (int k2 = 0; k2 < 8; ++k2) {                   // bin k = pcol + 25 k2 and its partner 200 - k = (25 - pcol) + 25 (7 - k2)
+          const float2 w = s.tw400[pcol + 25 * k2];
+          rfft_power_pair(a[k2], c[7 - k2], cmake(w.x, w.y), pw0[k2], pw0[8 + 7 - k2]);
         }
       }
     }
@@ -202,9 +208,8 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
       dft8(c);
 #pragma unroll
       for (int k2 = 0; k2 < 8; ++k2) {
-        const float2 w1 = s.tw400[pcol + 25 * k2], w2 = s.tw400[25 - pcol + 25 * k2];
-        pw1[k2] = rfft_power(a[k2], c[7 - k2], cmake(w1.x, w1.y));
-        pw1[8 + k2] = rfft_power(c[k2], a[7 - k2], cmake(w2.x, w2.y));
+        const float2 w = s.tw400[pcol + 25 * k2];
+        rfft_power_pair(a[k2], c[7 - k2], cmake(w.x, w.y), pw1[k2], pw1[8 + 7 - k2]);
       }
     }
   }
@@ -290,7 +295,7 @@ __global__ void mel_init_max_kernel(int* keys, int B) {
 // is a zero guard row for r == 0 and r == T_out + 1, frame r - 1 otherwise.  The last block of a chunk re-arms its max key.
 __global__ void __launch_bounds__(256)
 mel_finalize_kernel(const float* __restrict__ logmel, int* __restrict__ chunk_max_key, int n_frames, int T_out, int m,
-                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, unsigned int* __restrict__ done_counter) {
+                    float* __restrict__ out_f32, op16* __restrict__ out_bf16, unsigned int* __restrict__ done_counter) {
   const int b = blockIdx.y;
   const long long per_padded = static_cast<long long>(T_out + 2) * m;
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -315,8 +320,8 @@ mel_finalize_kernel(const float* __restrict__ logmel, int* __restrict__ chunk_ma
     }
     if (out_bf16) {
       uint2 w;
-      w.x = pack_bf16x2(v[0], v[1]);
-      w.y = pack_bf16x2(v[2], v[3]);
+      w.x = pack_op16x2(v[0], v[1]);
+      w.y = pack_op16x2(v[2], v[3]);
       *reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(b) * per_padded + i) = w;
     }
   }
@@ -380,7 +385,7 @@ int mel_init() {
     for (int n2 = 0; n2 < 8; ++n2)
       for (int k1 = 0; k1 < 25; ++k1) {
         double a = -2.0 * PI * n2 * k1 / 200.0;
-        tw200[n2 * 25 + k1] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+        tw200[n2 * 25 + k1] = make_float2(0.5f * static_cast<float>(cos(a)), 0.5f * static_cast<float>(sin(a)));   // pre-halved: rfft_power_pair
       }
     for (int k = 0; k <= NFREQ; ++k) {
       double a = -2.0 * PI * k / 400.0;
@@ -428,7 +433,7 @@ int launch_mel_stft(const MelBatch& job, const MelTables& t, float* logmel, int*
 }
 
 int launch_mel_finalize(const float* logmel, int* chunk_max_key, unsigned int* done_counter, int n_frames, int T_out, int n_mels, int B,
-                        float* out_f32, __nv_bfloat16* out_bf16_padded, cudaStream_t stream) {
+                        float* out_f32, op16* out_bf16_padded, cudaStream_t stream) {
   if (B <= 0 || T_out <= 0) return WB_OK;
   if (n_mels % 4 == 0) {
     const long long per_padded = static_cast<long long>(T_out + 2) * n_mels;
@@ -479,7 +484,7 @@ extern "C" void wb_debug_fft400_power_host(const float* y, float* p) {
     dft25(v, tw25);
     for (int k1 = 0; k1 < 25; ++k1) {
       double a = -2.0 * PI * n2 * k1 / 200.0;
-      z[n2 * 25 + k1] = cmul(v[k1], cmake(static_cast<float>(cos(a)), static_cast<float>(sin(a))));
+      z[n2 * 25 + k1] = cmul(v[k1], cmake(0.5f * static_cast<float>(cos(a)), 0.5f * static_cast<float>(sin(a))));   // Z / 2, as the kernel
     }
   }
   auto tw400 = [&](int k) {
@@ -491,18 +496,19 @@ extern "C" void wb_debug_fft400_power_host(const float* y, float* p) {
     for (int n2 = 0; n2 < 8; ++n2) a[n2] = z[n2 * 25 + pcol];
     dft8(a);
     if (pcol == 0) {
-      float r0 = a[0].x + a[0].y, r200 = a[0].x - a[0].y;
+      float r0 = 2.0f * (a[0].x + a[0].y), r200 = 2.0f * (a[0].x - a[0].y);
       p[0] = r0 * r0;
       p[200] = r200 * r200;
-      for (int k2 = 1; k2 < 8; ++k2) p[25 * k2] = rfft_power(a[k2], a[8 - k2], tw400(25 * k2));
+      for (int k2 = 1; k2 < 4; ++k2) rfft_power_pair(a[k2], a[8 - k2], tw400(25 * k2), p[25 * k2], p[200 - 25 * k2]);
+      float dummy;
+      rfft_power_pair(a[4], a[4], tw400(100), p[100], dummy);
     } else {
       cf c[8];
       for (int n2 = 0; n2 < 8; ++n2) c[n2] = z[n2 * 25 + 25 - pcol];
       dft8(c);
       for (int k2 = 0; k2 < 8; ++k2) {
-        int k = pcol + 25 * k2, kk = 25 - pcol + 25 * k2;
-        p[k] = rfft_power(a[k2], c[7 - k2], tw400(k));
-        p[kk] = rfft_power(c[k2], a[7 - k2], tw400(kk));
+        int k = pcol + 25 * k2;
+        rfft_power_pair(a[k2], c[7 - k2], tw400(k), p[k], p[200 - k]);
       }
     }
   }

@@ -25,7 +25,9 @@ constexpr int N_FRAMES_30S = 3000;      // lib.rs:409
 constexpr int N_POS_30S = 1500;         // conv2, stride 2 (encoder.rs:79)
 constexpr int N_FFT = 400, HOP = 160, N_FREQ = 201;
 
-typedef __nv_bfloat16 bf16;
+// internal output format of the encoder: 16-bit states in the OPERAND format (they feed the decoder's cross-attention K/V GEMM)
+constexpr wb_dtype WB_OP16 = static_cast<wb_dtype>(2);
+inline size_t dtype_size(wb_dtype dt) { return dt == WB_F32 ? 4 : 2; }
 
 template <typename T>
 struct DevBuf {
@@ -79,25 +81,25 @@ struct DeviceGuard {
 // One encoder block's device tensors.
 struct LayerW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
-  bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  op16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float* sqkv = nullptr;                 // [3d] per-column scale of the fused QKV GEMM (quantised files) or nullptr
   float so = 1.f, s1 = 1.f, s2 = 1.f;    // per-tensor scales (`.apr` scale table) of the other three GEMMs
   // per-channel int8 (model/quantized.rs:1769-1813): one scale per output row of W = per output column of the GEMM
   float *cso = nullptr, *cs1 = nullptr, *cs2 = nullptr;
   // Int8 / Int4 payloads stay PACKED in HBM (the file's own bytes: i8, or two's-complement nibbles, low nibble first);
-  // the bf16 pointers above then alias the replica's per-kind expansion buffers, refilled for every layer.
+  // the op16 pointers above then alias the replica's per-kind expansion buffers, refilled for every layer.
   uint8_t *pqkv = nullptr, *po = nullptr, *p1 = nullptr, *p2 = nullptr;
 };
 
 // One decoder block (src/model/decoder.rs DecoderBlock: ln1 / self_attn / ln2 / cross_attn / ln3 / ffn), f32 for the per-token path,
-// bf16 [2d][d] (k_proj rows then v_proj rows) for the cross-attention K/V precompute GEMM.
+// op16 [2d][d] (k_proj rows then v_proj rows) for the cross-attention K/V precompute GEMM.
 struct DecLayerW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *ln3_g = nullptr, *ln3_b = nullptr;
   float *sa_wqkv = nullptr, *sa_bqkv = nullptr;     // [3d][d], [3d]  (q | k | v rows)
   float *sa_wo = nullptr, *sa_bo = nullptr;
   float *ca_wq = nullptr, *ca_bq = nullptr, *ca_wo = nullptr, *ca_bo = nullptr;
-  bf16* ca_wkv = nullptr;                            // [2d][d]
+  op16* ca_wkv = nullptr;                            // [2d][d]
   float* ca_bkv = nullptr;                           // [2d]
   float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
 };
@@ -117,7 +119,7 @@ struct Workspace {
   DevBuf<float> audio, logmel, mel_f32, x, out_f32;
   DevBuf<int> n_valid, max_key;
   DevBuf<unsigned int> mel_done;        // [B] zeroed: mel_finalize's last-block protocol
-  DevBuf<bf16> mel_bf16, c1, xn, qkv, att, hid, out_bf16;
+  DevBuf<op16> mel_bf16, c1, xn, qkv, att, hid, out_bf16;
   int guard_T = -1;                     // T for which c1's zero guard rows (conv2's padding) are in place
 };
 
@@ -134,13 +136,13 @@ struct Replica {
   MelTables mel{};
   std::map<int, MelTables> htk_tables;  // BatchPreprocessor filterbanks by n_mels (built on first use)
   // conv stem
-  bf16 *conv1_w = nullptr, *conv2_w = nullptr;
+  op16 *conv1_w = nullptr, *conv2_w = nullptr;
   float *conv1_b = nullptr, *conv2_b = nullptr;
   float conv1_s = 1.f, conv2_s = 1.f;
   float* pe = nullptr;
   std::vector<LayerW> layers;
-  int quant = 0;                        // 0: bf16 weights resident; 2 / 3: int8 / int4 payloads resident, expanded per layer
-  bf16 *xp_qkv = nullptr, *xp_o = nullptr, *xp_1 = nullptr, *xp_2 = nullptr;   // expansion buffers (12 d^2 bf16: L2-sized)
+  int quant = 0;                        // 0: op16 weights resident; 2 / 3: int8 / int4 payloads resident, expanded per layer
+  op16 *xp_qkv = nullptr, *xp_o = nullptr, *xp_1 = nullptr, *xp_2 = nullptr;   // expansion buffers (12 d^2 op16: L2-sized)
   float *lnp_g = nullptr, *lnp_b = nullptr;
   DecoderW dec;
   Workspace ws;
@@ -255,12 +257,12 @@ int mel_compute_ragged(Replica* m, const MelTables& tab, const float* const* aud
 // ---- decoder.cu
 int load_decoder(Replica* m, const AprFile& f, struct Uploader& up);
 void free_decode_state(Replica* m);
-int decoder_cross_kv(Replica* m, const bf16* d_states, int B);
-int decoder_greedy(Replica* m, const bf16* d_states, int B, const int* initial_tokens, int n_init, int max_tokens, int suppress_timestamps,
+int decoder_cross_kv(Replica* m, const op16* d_states, int B);
+int decoder_greedy(Replica* m, const op16* d_states, int B, const int* initial_tokens, int n_init, int max_tokens, int suppress_timestamps,
                    int* tokens_out, int* lens_out);
-int decoder_greedy_s(Replica* m, const bf16* d_states, int B, int S, const int* initial_tokens, int n_init, int max_tokens,
+int decoder_greedy_s(Replica* m, const op16* d_states, int B, int S, const int* initial_tokens, int n_init, int max_tokens,
                      int suppress_timestamps, int* tokens_out, int* lens_out, float* logits_last_host);
-int decoder_debug_cross_kv(Replica* m, const bf16* d_states, int S, int layer, float* k_out, float* v_out);
+int decoder_debug_cross_kv(Replica* m, const op16* d_states, int S, int layer, float* k_out, float* v_out);
 
 }  // namespace wb
 

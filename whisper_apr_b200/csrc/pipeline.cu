@@ -47,8 +47,8 @@ int ensure_workspace(Replica* m, int B) {
 }
 
 // ---- encoder launch sequence ------------------------------------------------------------------------
-// Precondition: ws.mel_bf16 holds [B][T+2][n_mels] bf16 with rows 1..T = mel frames and zero guard rows.
-// d_out: [B][S][d] f32 or bf16 (device).  n_layers < 0 -> all layers; ln_post as Encoder::forward (encoder.rs:477).
+// Precondition: ws.mel_bf16 holds [B][T+2][n_mels] op16 with rows 1..T = mel frames and zero guard rows.
+// d_out: [B][S][d] f32 or op16 (device).  n_layers < 0 -> all layers; ln_post as Encoder::forward (encoder.rs:477).
 int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int n_layers, bool ln_post) {
   const int d = static_cast<int>(m->cfg.n_audio_state), nm = static_cast<int>(m->cfg.n_mels);
   const int H = static_cast<int>(m->cfg.n_audio_head);
@@ -62,7 +62,7 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   // c1 guard rows (0 and T+1 of every batch entry) are zero: conv2's padding.  conv1 only ever writes rows 1..T, so they stay zero
   // from one step to the next; they are re-laid only when T (the row pitch of the batch entries) changes.
   if (w.guard_T != T) {
-    WB_CUDA_OK(cudaMemsetAsync(w.c1.p, 0, w.c1.n * sizeof(bf16), st));
+    WB_CUDA_OK(cudaMemsetAsync(w.c1.p, 0, w.c1.n * sizeof(op16), st));
     w.guard_T = T;
   }
 
@@ -83,40 +83,43 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   WB_PROF(PC_GEMM, launch_gemm(g, st));
 
   const int M = B * S;
-  auto flat = [&](const bf16* A, int K, const bf16* W, int N, int epi, float alpha, const float* cs, const float* bias, void* out) {
+  auto flat = [&](const op16* A, int K, const op16* W, int N, int epi, float alpha, const float* cs, const float* bias, void* out) {
     GemmDesc q{};
     q.A = A; q.a_row_stride = K; q.a_batch_stride = static_cast<long long>(M) * K; q.rows_per_batch = M; q.n_batch = 1;
     q.W = W; q.N = N; q.K = K; q.epilogue = epi; q.alpha = alpha; q.col_scale = cs; q.bias = bias;
     q.out = out; q.ldc = N; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
     return launch_gemm(q, st);
   };
-  // Quantised models: a layer's packed weights are expanded to bf16 (exact integer values; the scale stays in the GEMM epilogue)
+  // Quantised models: a layer's packed weights are expanded to op16 (exact integer values; the scale stays in the GEMM epilogue)
   // right before the GEMM that consumes them, into buffers every layer reuses.  With M = B x 1500 rows per launch each weight tile
   // is consumed by ~190 row tiles, so expanding once per launch costs 1/190th of converting inside every CTA, and the 12 d^2
-  // bf16 (39 MB for d = 1280) stay L2-resident for the GEMM that follows; HBM only ever holds the packed bytes.
+  // op16 (39 MB for d = 1280) stay L2-resident for the GEMM that follows; HBM only ever holds the packed bytes.
   const size_t dd = static_cast<size_t>(d) * d;
-  auto expand = [&](const uint8_t* packed, bf16* dst, size_t n) {
-    return m->quant == 2 ? launch_i8_to_bf16(reinterpret_cast<const int8_t*>(packed), dst, n, st) : launch_i4_to_bf16(packed, dst, n, st);
+  auto expand = [&](const uint8_t* packed, op16* dst, size_t n) {
+    return m->quant == 2 ? launch_i8_to_op16(reinterpret_cast<const int8_t*>(packed), dst, n, st) : launch_i4_to_op16(packed, dst, n, st);
   };
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = m->layers[i];
-    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, nullptr, st));
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, false, nullptr, st));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.pqkv, lw.wqkv, 3 * dd)); }
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p));
     WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.po, lw.wo, dd)); }
     WB_PROF(PC_GEMM, flat(w.att.p, d, lw.wo, d, EPI_RESID_F32, lw.so, lw.cso, lw.bo, w.x.p));
-    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln2_g, lw.ln2_b, M, d, w.xn.p, nullptr, st));
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln2_g, lw.ln2_b, M, d, w.xn.p, false, nullptr, st));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p1, lw.w1, 4 * dd)); }
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.w1, 4 * d, EPI_GELU_BF16, lw.s1, lw.cs1, lw.b1, w.hid.p));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p2, lw.w2, 4 * dd)); }
     WB_PROF(PC_GEMM, flat(w.hid.p, 4 * d, lw.w2, d, EPI_RESID_F32, lw.s2, lw.cs2, lw.b2, w.x.p));
   }
   if (ln_post) {
-    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, m->lnp_g, m->lnp_b, M, d, out_dtype == WB_BF16 ? static_cast<bf16*>(d_out) : nullptr,
-                                           out_dtype == WB_BF16 ? nullptr : static_cast<float*>(d_out), st));
+    // 16-bit states: bf16 when the caller asked for WB_BF16 (a user-facing format), the operand format when they feed the decoder's
+    // cross-attention K/V GEMM (WB_OP16, internal)
+    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, m->lnp_g, m->lnp_b, M, d, out_dtype != WB_F32 ? d_out : nullptr, out_dtype == WB_BF16,
+                                           out_dtype == WB_F32 ? static_cast<float*>(d_out) : nullptr, st));
   } else {
-    if (out_dtype == WB_BF16) rc = launch_f32_to_bf16(w.x.p, static_cast<bf16*>(d_out), static_cast<size_t>(M) * d, st);
+    if (out_dtype == WB_BF16) return set_error(WB_ERR_MODEL, "truncated encodes are f32 only");
+    if (out_dtype == WB_OP16) rc = launch_f32_to_op16(w.x.p, static_cast<op16*>(d_out), static_cast<size_t>(M) * d, st);
     else {
       WB_CUDA_OK(cudaMemcpyAsync(d_out, w.x.p, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, st));
     }
@@ -126,7 +129,7 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
 }
 
 // mel of B chunks already in ws.audio ([B][480000], n_valid per chunk in ws.n_valid) -> optional f32 [B][3000][m] and/or
-// the bf16 padded operand in ws.mel_bf16.
+// the op16 padded operand in ws.mel_bf16.
 int mel_device(Replica* m, const float* d_audio, long long audio_stride, const long long* d_seg_off, const int* d_n_valid, int B,
                float* d_mel_f32, bool want_bf16) {
   Workspace& w = m->ws;
@@ -194,7 +197,7 @@ int encode_same_len(Replica* m, const float* const* mels, const float* d_mel, in
   // B mels of T frames each (host pointers `mels` or one device array `d_mel` [B][T][nm]) -> [B][S][d]
   const int nm = static_cast<int>(m->cfg.n_mels), d = static_cast<int>(m->cfg.n_audio_state);
   const int S = (T - 1) / 2 + 1;
-  const size_t esz = dt == WB_BF16 ? 2 : 4;
+  const size_t esz = dtype_size(dt);
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = std::min(m->max_batch, B - b0);
     int rc = ensure_workspace(m, nb);
@@ -208,10 +211,10 @@ int encode_same_len(Replica* m, const float* const* mels, const float* d_mel, in
                                    cudaMemcpyHostToDevice, m->stream));
       src_dev = m->ws.mel_f32.p;
     }
-    if ((rc = launch_mel_pad_bf16(src_dev, m->ws.mel_bf16.p, nb, T, nm, m->stream)) != WB_OK) return rc;
+    if ((rc = launch_mel_pad_op16(src_dev, m->ws.mel_bf16.p, nb, T, nm, m->stream)) != WB_OK) return rc;
     void* dst_dev;
     if (out_dev) dst_dev = static_cast<uint8_t*>(out_dev) + static_cast<size_t>(b0) * out_stride_elems * esz;
-    else dst_dev = dt == WB_BF16 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
+    else dst_dev = dt != WB_F32 ? static_cast<void*>(m->ws.out_bf16.p) : static_cast<void*>(m->ws.out_f32.p);
     if ((rc = encode_device(m, nb, T, dst_dev, dt, n_layers, ln_post)) != WB_OK) return rc;
     if (out_host) {
       const size_t row_bytes = static_cast<size_t>(S) * d * esz;
@@ -327,7 +330,7 @@ int prepare_slot(Replica* m, Replica::Slot& sl, int nb, size_t out_bytes) {
 int enqueue_microbatch(Replica* m, const float* const* audio, const size_t* n_samples, int nb, void* out_host, void* d_out_final,
                        wb_dtype out_dtype) {
   int rc;
-  const size_t d = m->cfg.n_audio_state, S = N_POS_30S, esz = out_dtype == WB_BF16 ? 2 : 4;
+  const size_t d = m->cfg.n_audio_state, S = N_POS_30S, esz = dtype_size(out_dtype);
   const size_t out_bytes = static_cast<size_t>(nb) * S * d * esz;
   Replica::Slot& sl = m->slot[m->next_slot];
   m->next_slot ^= 1;

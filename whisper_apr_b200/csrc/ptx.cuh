@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace wb {
@@ -268,11 +270,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: bf16 x bf16 -> f32, M x N tile.
-//   [4,6) D format (1 = f32) | [7,10) A format (1 = bf16) | [10,13) B format (1 = bf16)
+// Instruction descriptor, kind::f16: op16 x op16 -> f32, M x N tile (op16 = fp16 or bf16; A and B must share the format).
+//   [4,6) D format (1 = f32) | [7,10) A format (0 = f16, 1 = bf16) | [10,13) B format (same codes)
 //   [15] A major (0 = K) | [16] B major (0 = K, 1 = MN) | [17,23) N >> 3 | [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+#ifdef WB_OPERANDS_BF16
+constexpr uint32_t kIdescOp16Fmt = 1u;
+#else
+constexpr uint32_t kIdescOp16Fmt = 0u;
+#endif
+__host__ __device__ constexpr uint32_t umma_idesc_op16(int M, int N, int b_mn_major) {
+  return (1u << 4) | (kIdescOp16Fmt << 7) | (kIdescOp16Fmt << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
@@ -326,6 +333,30 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// two f32 -> two 16-bit OPERAND values (fp16, or bf16 with -DWB_OPERANDS_BF16: wb_internal.h), low half first; one F2FP either way
+__device__ __forceinline__ uint32_t pack_op16x2(float lo, float hi) {
+#ifdef WB_OPERANDS_BF16
+  return pack_bf16x2(lo, hi);
+#else
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+#endif
+}
+// the two halves of a packed operand pair as f32
+__device__ __forceinline__ float unpack_op16_lo(uint32_t w) {
+#ifdef WB_OPERANDS_BF16
+  return __uint_as_float(w << 16);
+#else
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu)));
+#endif
+}
+__device__ __forceinline__ float unpack_op16_hi(uint32_t w) {
+#ifdef WB_OPERANDS_BF16
+  return __uint_as_float(w & 0xffff0000u);
+#else
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16)));
+#endif
 }
 
 }  // namespace wb

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -13,6 +14,26 @@
 #include "../../include/whisper_b200.h"
 
 namespace wb {
+
+// ---- the 16-bit operand format of every tensor-core product (GEMM A / W, attention Q / K / V / P) and of every activation that feeds
+// one.  IEEE fp16 by default: both formats run tcgen05.mma kind::f16 at the same rate and move the same bytes, but fp16 keeps an 11-bit
+// significand against bf16's 8.  With bf16 the weight rounding alone costs 1.5e-2 of the 2e-2 max-abs parity gate after 32 layers
+// (profiles/r02_bf16_error_budget.txt: three chunks measured 1.91e-2 .. 2.03e-2); Whisper's value ranges sit far inside fp16's
+// (fp16 is the reference implementations' own inference format).  -DWB_OPERANDS_BF16 builds the bf16 variant (the A and B formats of a
+// kind::f16 MMA cannot be mixed: bf16 x fp16 raises an illegal-instruction fault on the B200).
+#ifdef WB_OPERANDS_BF16
+typedef __nv_bfloat16 op16;
+constexpr uint32_t kOp16Format = 1;        // F16F32Format::BF16 of the instruction descriptor
+constexpr bool kOp16IsFp16 = false;
+__host__ __device__ inline float op16_to_float(op16 v) { return __bfloat162float(v); }
+__host__ __device__ inline op16 float_to_op16(float v) { return __float2bfloat16_rn(v); }
+#else
+typedef __half op16;
+constexpr uint32_t kOp16Format = 0;        // F16F32Format::F16
+constexpr bool kOp16IsFp16 = true;
+__host__ __device__ inline float op16_to_float(op16 v) { return __half2float(v); }
+__host__ __device__ inline op16 float_to_op16(float v) { return __float2half_rn(v); }
+#endif
 
 // ---- error plumbing (mirrors WhisperError::{Audio,Model,Format}, src/error.rs:6-44)
 int set_error(int status, const std::string& msg);   // returns status
@@ -67,13 +88,13 @@ enum GemmEpilogue : int {
 
 struct GemmDesc {
   // A operand: bf16, viewed as [n_batch][rows_per_batch][K] with arbitrary (16 B aligned) strides.
-  const __nv_bfloat16* A;
+  const op16* A;
   long long a_row_stride;     // elements between consecutive rows
   long long a_batch_stride;   // elements between consecutive batch entries
   int rows_per_batch;
   int n_batch;
   // W operand: bf16 [N][K] row-major (the reference's [out][in] layout, attention.rs:33-34)
-  const __nv_bfloat16* W;
+  const op16* W;
   int N, K;
   // epilogue
   int epilogue;
@@ -88,11 +109,11 @@ struct GemmDesc {
 };
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
 int gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
-int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
 
 // ---- attention: qkv bf16 [B][S][3d] (q | k | v column blocks) -> out bf16 [B][S][d]
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int d, int n_heads, cudaStream_t stream);
+int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream);
 int attention_init();
 
 // ---- mel
@@ -133,24 +154,24 @@ int launch_mel_init_keys(int* keys, int B, cudaStream_t stream);
 // clamp/scale/pad: out_f32 [B][T_out][m] (optional), out_bf16 [B][T_out+2][m] with its two zero guard rows (optional).
 // done_counter: [B] zero-initialised scratch of the "last block re-arms the key" protocol.
 int launch_mel_finalize(const float* logmel, int* chunk_max_key, unsigned int* done_counter, int n_frames, int T_out, int n_mels, int B,
-                        float* out_f32, __nv_bfloat16* out_bf16_padded, cudaStream_t stream);
+                        float* out_f32, op16* out_bf16_padded, cudaStream_t stream);
 // ragged segments, in place allowed (out may alias logmel); keys are NOT re-armed
 int launch_mel_finalize_ragged(const float* logmel, const int* max_keys, const int* n_frames_arr, const long long* row_off, int n_mels, int B,
                                long long max_rows, float* out, cudaStream_t stream);
 int mel_init();
 
 // ---- elementwise / normalisation
-int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, void* out_16, bool out_16_is_bf16,
                      float* out_f32, cudaStream_t stream);
-int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
-int launch_i8_to_bf16(const int8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
-int launch_i4_to_bf16(const uint8_t* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+int launch_f32_to_op16(const float* in, op16* out, size_t n, cudaStream_t stream);
+int launch_i8_to_op16(const int8_t* in, op16* out, size_t n, cudaStream_t stream);
+int launch_i4_to_op16(const uint8_t* in, op16* out, size_t n, cudaStream_t stream);
 int launch_i8_to_f32(const int8_t* in, float scale, float* out, size_t n, cudaStream_t stream);
 int launch_i4_to_f32(const uint8_t* in, float scale, float* out, size_t n, cudaStream_t stream);
 // conv weight [out][in][3] (any of f32/int8/int4 already expanded to bf16) -> [out][3][in]
-int launch_conv_repack(const __nv_bfloat16* in, __nv_bfloat16* out, int c_out, int c_in, cudaStream_t stream);
+int launch_conv_repack(const op16* in, op16* out, int c_out, int c_in, cudaStream_t stream);
 // mel f32 [B][T][m] -> bf16 [B][T+2][m] with zero rows 0 and T+1
-int launch_mel_pad_bf16(const float* mel, __nv_bfloat16* out, int B, int T, int m, cudaStream_t stream);
-int launch_fill_bf16_rows(__nv_bfloat16* base, long long batch_stride, int B, int row_elems, cudaStream_t stream);
+int launch_mel_pad_op16(const float* mel, op16* out, int B, int T, int m, cudaStream_t stream);
+int launch_fill_op16_rows(op16* base, long long batch_stride, int B, int row_elems, cudaStream_t stream);
 
 }  // namespace wb
