@@ -429,7 +429,7 @@ def main():
     parity = None
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "parity_depth.json")))
-        key = {"large-v3": "large-v3 32L bf16 B=32", "base": "base 6L bf16 B=64", "small": "small 12L int8", "medium": "medium 24L int4"}.get(args.model)
+        key = {"large-v3": "large-v3 32L B=32", "base": "base 6L B=64", "small": "small 12L int8", "medium": "medium 24L int4"}.get(args.model)
         if key in rec:
             fin = rec[key]["final"]
             first = fin.get("pos0", fin)

@@ -115,7 +115,7 @@ def test_large_v3_full_depth_bf16_batch32():
         print(f"[large-v3 audio {s}] max-abs {e.max():.4e} rms {np.sqrt((e ** 2).mean()):.3e} cos {res[f'audio{s}']['cos']:.7f}")
     e0 = np.abs(out[0] - ref)
     res["pos0"]["rms"] = float(np.sqrt((e0 ** 2).mean()))
-    _record("large-v3 32L bf16 B=32", {"final": res, "depth": growth, "oracle": "numpy float32, naive softmax attention", "oracle_s": round(t_oracle, 1),
+    _record("large-v3 32L B=32", {"operand_format": __import__("whisper_apr_b200")._lib.lib().wb_operand_format().decode(), "final": res, "depth": growth, "oracle": "numpy float32, naive softmax attention", "oracle_s": round(t_oracle, 1),
                                        "load_s": round(t_load, 1), "gate": {"max_abs": ENC_TOL, "cos": ENC_COS}})
     for s in (105, 106):
         assert res[f"audio{s}"]["max_abs"] <= ENC_TOL and res[f"audio{s}"]["cos"] >= ENC_COS, res
@@ -161,5 +161,5 @@ def test_base_batch64_positions():
         res[f"pos{pos}"] = {"max_abs": err, "cos": cos}
         assert err <= ENC_TOL and cos >= ENC_COS
     assert np.array_equal(out[0], out[63])
-    _record("base 6L bf16 B=64", {"final": res})
+    _record("base 6L B=64", {"final": res})
     model.close()

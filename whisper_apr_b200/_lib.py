@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwhisper_b200.so")
+LIB_PATH = os.environ.get("WB_LIB_PATH") or os.path.join(_HERE, "libwhisper_b200.so")     # WB_LIB_PATH: A/B builds (e.g. the bf16-operand variant)
 
 WB_OK, WB_ERR_AUDIO, WB_ERR_MODEL, WB_ERR_FORMAT, WB_ERR_CUDA = 0, 1, 2, 3, 4
 WB_F32, WB_BF16 = 0, 1

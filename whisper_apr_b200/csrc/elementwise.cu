@@ -10,26 +10,24 @@ namespace {
 // LayerNorm::forward (src/model/encoder.rs:219-251): per row mean, POPULATION variance (two passes, as the
 // reference), 1/sqrt(var + 1e-5), * gamma + beta.  One warp per row; the row lives in registers between the
 // passes so x is read from HBM once (4 B/elem in, 2 B/elem out for the bf16 GEMM operand).
-template <int NP>   // pairs of float4 (8 consecutive elements) per lane; d == 8 * n_pairs, n_pairs <= 32 * NP
+template <int NV>   // float4 per lane; d == 128 * nv, nv <= NV
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d,
                  uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const int n_pairs = d >> 3;
-  // a lane owns 8 consecutive elements per step: 32 B loads, and a 16 B bf16 store -- the widest a lane can issue, which is what
-  // keeps the store stream efficient when `out` is a PEER device's memory (the gather writes the final states over NVLink)
+  const int nv = d >> 7;
+  // lane l owns float4 l, l + 32, ...: every load instruction of the warp covers 512 contiguous bytes (a lane reading 32 B runs
+  // instead -- tried for 16 B output stores -- touches every sector twice and cost 8 % on this HBM-bound kernel)
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
-  float4 v[NP][2];
+  float4 v[NV];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    const int p = lane + 32 * i;
-    if (p < n_pairs) {
-      v[i][0] = xr[2 * p];
-      v[i][1] = xr[2 * p + 1];
-      sum += ((v[i][0].x + v[i][0].y) + (v[i][0].z + v[i][0].w)) + ((v[i][1].x + v[i][1].y) + (v[i][1].z + v[i][1].w));
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      v[i] = xr[lane + 32 * i];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
 #pragma unroll
@@ -37,13 +35,10 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   const float mean = sum / static_cast<float>(d);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    if (lane + 32 * i < n_pairs) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float a = v[i][h].x - mean, b = v[i][h].y - mean, c = v[i][h].z - mean, e = v[i][h].w - mean;
-        sq += (a * a + b * b) + (c * c + e * e);
-      }
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + e * e);
     }
   }
 #pragma unroll
@@ -52,38 +47,26 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    const int p = lane + 32 * i;
-    if (p < n_pairs) {
-      float4 r[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 g = __ldg(g4 + 2 * p + h), bb = __ldg(b4 + 2 * p + h);
-        r[h].x = (v[i][h].x - mean) * inv * g.x + bb.x;
-        r[h].y = (v[i][h].y - mean) * inv * g.y + bb.y;
-        r[h].z = (v[i][h].z - mean) * inv * g.z + bb.z;
-        r[h].w = (v[i][h].w - mean) * inv * g.w + bb.w;
-      }
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      const float4 g = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+      float4 r;
+      r.x = (v[i].x - mean) * inv * g.x + bb.x;
+      r.y = (v[i].y - mean) * inv * g.y + bb.y;
+      r.z = (v[i].z - mean) * inv * g.z + bb.z;
+      r.w = (v[i].w - mean) * inv * g.w + bb.w;
       if (out_16) {
-        uint4 w;
+        uint2 w;
         if (as_bf16) {             // the caller asked for bf16 states (WB_BF16): a user-facing format, not the operand format
-          w.x = pack_bf16x2(r[0].x, r[0].y);
-          w.y = pack_bf16x2(r[0].z, r[0].w);
-          w.z = pack_bf16x2(r[1].x, r[1].y);
-          w.w = pack_bf16x2(r[1].z, r[1].w);
+          w.x = pack_bf16x2(r.x, r.y);
+          w.y = pack_bf16x2(r.z, r.w);
         } else {
-          w.x = pack_op16x2(r[0].x, r[0].y);
-          w.y = pack_op16x2(r[0].z, r[0].w);
-          w.z = pack_op16x2(r[1].x, r[1].y);
-          w.w = pack_op16x2(r[1].z, r[1].w);
+          w.x = pack_op16x2(r.x, r.y);
+          w.y = pack_op16x2(r.z, r.w);
         }
-        reinterpret_cast<uint4*>(out_16 + static_cast<long long>(row) * d)[p] = w;
+        reinterpret_cast<uint2*>(out_16 + static_cast<long long>(row) * d)[lane + 32 * i] = w;
       }
-      if (out_f32) {
-        float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * d);
-        o[2 * p] = r[0];
-        o[2 * p + 1] = r[1];
-      }
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * d)[lane + 32 * i] = r;
     }
   }
 }
@@ -229,9 +212,9 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
   if (d % 128 == 0 && d <= 2048) {
-    if (d <= 512) layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
-    else if (d <= 1280) layernorm_kernel<5><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
-    else layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
+    if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
+    else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
+    else layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
     count_launch();
   } else {
     layernorm_generic_kernel<<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
