@@ -50,6 +50,7 @@ struct AttnTmParams {
   float scale_log2;
   op16* out;
   int use_token;
+  uint32_t rt_zero;                   // 0, but only known at run time (exp_row's ordering trick)
 };
 
 __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int& q0, int& h, int& b) {
@@ -80,18 +81,65 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 // warp per scheduler, 13 with two.  The microbenchmark keeps 8 exponentials between producer and consumer and reaches the pipe rate.
 // ncu: a lone warp per scheduler issues back-to-back MUFU.EX2 every ~9.5 cycles (8 with two warps), and ptxas places each
 // FADD two instructions behind the MUFU pair it consumes, so the phase runs at ~11 cycles per exponential (72 % of the pipe).
-__device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb) {
+// 2^x on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f with the round-to-nearest magic constant, a degree-3 polynomial
+// for 2^f on [-0.5, 0.5] (max relative error 1.9e-4, under half an ulp of the fp16 P it is rounded to) and the exponent added as an
+// integer.  9 issue slots against one MUFU.EX2 that occupies its pipe for 8 cycles: worth it for a FRACTION of the row, where
+// the independent FMA work fills the slots a lone warp otherwise spends waiting on the MUFU results it has just issued.
+__device__ __forceinline__ float exp2_fma_pipe(float x) {
+  x = fmaxf(x, -125.0f);                                   // exponent stays in range; masked keys (-inf) -> 2^-125 * ~1 ~ 0 in fp16
+  const float t = x + 12582912.0f;                         // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.055875536f, 0.24229462f);
+  p = fmaf(p, f, 0.6931273f);
+  p = fmaf(p, f, 0.99994826f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int POLY>   // 0: every exponential on the MUFU; n > 0: one pair in n goes to the FMA pipe instead; n < 0: MUFU only, consumers lag
+__device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb, uint32_t rt_zero) {
   float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (POLY >= 0) {
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    const float e0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), c, -mb));         // exp2(-inf) == 0: masked keys contribute nothing
-    const float e1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), c, -mb));
-    rs4[i & 3] += e0 + e1;
-    pk[i] = pack_op16x2(e0, e1);
+    for (int i = 0; i < 64; ++i) {
+      const float x0 = fmaf(__uint_as_float(s[2 * i]), c, -mb), x1 = fmaf(__uint_as_float(s[2 * i + 1]), c, -mb);
+      float e0, e1;
+      constexpr int PERIOD = POLY > 0 ? POLY : 1;
+      if (POLY > 0 && (i % PERIOD) == PERIOD - 1) {
+        e0 = exp2_fma_pipe(x0);
+        e1 = exp2_fma_pipe(x1);
+      } else {
+        e0 = fast_exp2(x0);                                  // exp2(-inf) == 0: masked keys contribute nothing
+        e1 = fast_exp2(x1);
+      }
+      rs4[i & 3] += e0 + e1;
+      pk[i] = pack_op16x2(e0, e1);
+    }
+  } else {
+    // consumers LAG = -POLY pairs behind their exponentials, with a true dependence that keeps ptxas from re-pairing them: the sum of
+    // pair i takes its second operand through a select on a value of pair i + LAG (always false: exponentials are never negative)
+    constexpr int LAG = -POLY;
+    float e[128];
+#pragma unroll
+    for (int i = 0; i < 64 + LAG; ++i) {
+      if (i < 64) {
+        e[2 * i] = fast_exp2(fmaf(__uint_as_float(s[2 * i]), c, -mb));
+        e[2 * i + 1] = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), c, -mb));
+      }
+      if (i >= LAG) {
+        const int j = i - LAG;
+        float b = e[2 * j + 1];
+        // b | (bits(e of pair i) & 0): one LOP3 whose third operand is a RUN-TIME zero, so neither nvcc nor ptxas can drop the
+        // dependence -- the sum of pair j is ordered after the exponentials of pair i = j + LAG
+        if (i < 64) b = __uint_as_float(__float_as_uint(b) | (__float_as_uint(e[2 * i + 1]) & rt_zero));
+        rs4[j & 3] += e[2 * j] + b;
+        pk[j] = pack_op16x2(e[2 * j], e[2 * j + 1]);
+      }
+    }
   }
   return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -273,7 +321,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
         // ping-pong token: MUFU phases of the two warpgroups alternate
         if (p.use_token) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
         uint32_t pk[64];
-        const float rsum = exp_row(s, pk, c, mb);
+        const float rsum = exp_row<POLY>(s, pk, c, mb, p.rt_zero);
         if (p.use_token && !(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
         l_run = l_run * alpha + rsum;
         if (!pv_ok) mbar_wait(&pv_done[t], (g - 1) & 1u);    // PV of the previous block has read P_t
@@ -329,7 +377,9 @@ PerDeviceOnce g_tm_once;
 
 int attention_init() {
   return g_tm_once.run([](int) -> int {
-    WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+    WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+    WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+    WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel<-2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
     return WB_OK;
   });
 }
@@ -353,9 +403,20 @@ int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_head
   p.out = out;
   static const int no_token = getenv("WB_ATTN_NOTOKEN") != nullptr;       // tuning switch
   p.use_token = no_token ? 0 : 1;
+  p.rt_zero = 0;
   const int sms = device_sm_count();
   const int grid = p.n_items < sms ? p.n_items : sms;
-  attention_tm_kernel<<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p);
+  // Tuning switch, round 2 (profiles/r02g_attention_variants.txt, ms per launch alone, 32 x 20 x 1500 x 1500): default 0.514;
+  // WB_ATTN_POLY=8 / 6 / 4 (one pair in 8 / 6 / 4 through exp2_fma_pipe): 0.530 / 0.539 / 0.561; -2 / -4 (consumers forced 2 / 4 pairs
+  // behind their exponentials by a true dependence): 0.520 / 0.519.  Neither fewer MUFU operations nor a longer producer-consumer
+  // distance shortens the phase: it runs at ~81 % of the MUFU pipe's rate at the clock of the run (2530 of 2048 cycles per 256 x 128
+  // scores) and the remainder is the hand-over between the two alternating warpgroups, not the instruction mix inside the phase.
+  static const int poly = getenv("WB_ATTN_POLY") ? atoi(getenv("WB_ATTN_POLY")) : 0;
+  switch (poly) {
+    case 8: attention_tm_kernel<8><<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p); break;
+    case -2: attention_tm_kernel<-2><<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p); break;
+    default: attention_tm_kernel<0><<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p); break;
+  }
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
