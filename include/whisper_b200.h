@@ -253,6 +253,11 @@ int wb_vad_detect_batch(const wb_model* m, const float* const* audio, const size
 int wb_stream_encode_views(const wb_model* m, const float* const* streams, const size_t* stream_lens, int n_streams, size_t chunk_size,
                            size_t overlap, void* out, wb_dtype out_dtype, size_t out_capacity_chunks, size_t* chunk_counts,
                            size_t* total_chunks);
+/* Device-resident form of the same work (per-kernel measurement, and callers whose streams already live in HBM): d_arena holds the
+ * streams, d_seg_off[i] / d_n_valid[i] are chunk i's first sample (element offset into d_arena) and length.  Asynchronous on the
+ * model's stream. */
+int wb_mel_encode_views_dev(const wb_model* m, const float* d_arena, const long long* d_seg_off, const int* d_n_valid, int n_chunks,
+                            void* d_out, wb_dtype out_dtype);
 /* The chunk-assembly half of StreamingProcessor (src/audio/streaming.rs) for n_streams streams whose accumulators live in HBM:
  * push = push_audio (:672-675); ready = has_chunk; encode = get_chunk (:843-870: [carried overlap | samples] zero padded to the chunk
  * size, the chunk's last overlap_samples kept as the next chunk's prefix) -- or flush (:872-905) for every stream holding fresh audio --

@@ -100,6 +100,7 @@ SIGNATURES.update({
     "wb_vad_config_default": (None, [C.POINTER(WbVadConfig)]),
     "wb_vad_detect_batch": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, C.POINTER(WbVadConfig), _vp, C.c_int, _vp, C.POINTER(_vp), _szp]),
     "wb_stream_encode_views": (C.c_int, [_vp, C.POINTER(_vp), _szp, C.c_int, C.c_size_t, C.c_size_t, _vp, C.c_int, C.c_size_t, _szp, _szp]),
+    "wb_mel_encode_views_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int]),
     "wb_stream_set_new": (C.c_int, [_vp, C.c_int, C.c_size_t, C.c_size_t, C.POINTER(_vp)]),
     "wb_stream_set_free": (None, [_vp]),
     "wb_stream_set_push": (C.c_int, [_vp, _vp, C.POINTER(_vp), _szp, C.c_int]),

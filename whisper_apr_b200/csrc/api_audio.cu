@@ -294,6 +294,28 @@ int wb_stream_encode_views(const wb_model* ch, const float* const* streams, cons
   return WB_OK;
 }
 
+// The device-resident form: the streams already sit in HBM (d_arena), d_seg_off / d_n_valid describe n_chunks views into them.
+// Enqueues on the model's stream, does not synchronise.  d_out: [n_chunks][1500][d].
+int wb_mel_encode_views_dev(const wb_model* h, const float* d_arena, const long long* d_seg_off, const int* d_n_valid, int n_chunks,
+                            void* d_out, wb_dtype out_dtype) {
+  Replica* m = rep0(h);
+  if (!m || !d_arena || !d_seg_off || !d_n_valid || !d_out || n_chunks < 0) return set_error(WB_ERR_MODEL, "null argument");
+  if (out_dtype != WB_F32 && out_dtype != WB_BF16) return set_error(WB_ERR_MODEL, "output dtype must be WB_F32 or WB_BF16");
+  int rc = check_fused_dims(m);
+  if (rc != WB_OK) return rc;
+  std::lock_guard<std::mutex> lk(m->mu);
+  DeviceGuard guard(m->device);
+  const size_t per = static_cast<size_t>(N_POS_30S) * m->cfg.n_audio_state * dtype_size(out_dtype);
+  for (int c0 = 0; c0 < n_chunks; c0 += m->max_batch) {
+    const int nb = std::min(m->max_batch, n_chunks - c0);
+    if ((rc = ensure_workspace(m, nb)) != WB_OK) return rc;
+    if ((rc = mel_encode_step(m, d_arena, 0, d_seg_off + c0, d_n_valid + c0, nb, static_cast<uint8_t*>(d_out) + static_cast<size_t>(c0) * per,
+                              out_dtype)) != WB_OK)
+      return rc;
+  }
+  return WB_OK;
+}
+
 // ------------------------------------------------------------------------------- streaming chunk assembly
 int wb_stream_set_new(const wb_model* ch, int n_streams, size_t chunk_samples, size_t overlap_samples, wb_stream_set** out) {
   wb_model* h = const_cast<wb_model*>(ch);
