@@ -256,13 +256,20 @@ int upload_mel_tables(Replica* m, const std::vector<float>& filt, int n_mels, Me
   out->n_mels = n_mels;
   out->packed = nullptr;
   out->span_off = nullptr;
+  out->packed_lo = nullptr;
+  out->packed_len = nullptr;
   out->nnz = 0;
   std::vector<int> off(n_mels, 0);
   std::vector<float> packed;
-  for (int j = 0; j < n_mels; ++j) {                      // every span padded with zero weights to a multiple of 4 (16 B loads)
+  std::vector<int> plo(n_mels, 0), plen(n_mels, 0);
+  for (int j = 0; j < n_mels; ++j) {                      // every span widened with zero weights to 4-aligned bin bounds (16 B loads)
     off[j] = static_cast<int>(packed.size());
-    for (int k = 0; k < len[j]; ++k) packed.push_back(filt[static_cast<size_t>(j) * N_FREQ + lo[j] + k]);
-    while (packed.size() % 4 != 0) packed.push_back(0.0f);
+    if (len[j] == 0) continue;
+    plo[j] = lo[j] & ~3;
+    const int hi = (lo[j] + len[j] + 3) & ~3;           // <= 204: the kernel keeps bins 201..203 of every power row at zero
+    plen[j] = hi - plo[j];
+    for (int k = plo[j]; k < hi; ++k)
+      packed.push_back((k >= lo[j] && k < lo[j] + len[j]) ? filt[static_cast<size_t>(j) * N_FREQ + k] : 0.0f);
   }
   if (n_mels <= 256 && packed.size() <= 2048 && !packed.empty()) {
     float* d_packed;
@@ -271,8 +278,14 @@ int upload_mel_tables(Replica* m, const std::vector<float>& filt, int n_mels, Me
     if ((rc = dev_alloc(m, off.size(), &d_off)) != WB_OK) return rc;
     WB_CUDA_OK(cudaMemcpy(d_packed, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
     WB_CUDA_OK(cudaMemcpy(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    int *d_plo, *d_plen;
+    if ((rc = dev_alloc(m, plo.size(), &d_plo)) != WB_OK || (rc = dev_alloc(m, plen.size(), &d_plen)) != WB_OK) return rc;
+    WB_CUDA_OK(cudaMemcpy(d_plo, plo.data(), plo.size() * 4, cudaMemcpyHostToDevice));
+    WB_CUDA_OK(cudaMemcpy(d_plen, plen.data(), plen.size() * 4, cudaMemcpyHostToDevice));
     out->packed = d_packed;
     out->span_off = d_off;
+    out->packed_lo = d_plo;
+    out->packed_len = d_plen;
     out->nnz = static_cast<int>(packed.size());
   }
   return WB_OK;

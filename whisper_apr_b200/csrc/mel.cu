@@ -81,7 +81,7 @@ struct MelKParams {
   int* max_key;
 };
 
-__global__ void __launch_bounds__(MEL_THREADS, 2)
+__global__ void __launch_bounds__(MEL_THREADS, 3)
 mel_stft_kernel(const MelKParams p, const MelTables tab) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   MelSmem& s = *reinterpret_cast<MelSmem*>(smem_raw);
@@ -111,8 +111,8 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   if (fb_smem) {
     for (int i = tid; i < tab.nnz; i += MEL_THREADS) s.fbw[i] = __ldg(tab.packed + i);
     for (int i = tid; i < tab.n_mels; i += MEL_THREADS) {
-      s.fb_lo[i] = __ldg(tab.span_lo + i);
-      s.fb_len[i] = __ldg(tab.span_len + i);
+      s.fb_lo[i] = __ldg(tab.packed_lo + i);
+      s.fb_len[i] = __ldg(tab.packed_len + i);
       s.fb_off[i] = __ldg(tab.span_off + i);
     }
   }
@@ -131,21 +131,36 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   {
     cf v[25];
     const long long base = static_cast<long long>(f) * hop + 2 * n2;
-    const bool vec = (reinterpret_cast<uintptr_t>(seg + base) & 7) == 0;
+    const float* fp = seg + base;
+    // fast path (warp-uniform): every frame of the warp is live, lies inside the valid samples and is 8-byte aligned -> 25 plain
+    // float2 loads at immediate offsets; otherwise per-element bounds checks (segment tails, odd view offsets, the padded zone)
+    const bool easy = live && (base - 2 * n2 + NFFT <= n_valid) && ((reinterpret_cast<uintptr_t>(fp) & 7) == 0);
+    if (__all_sync(0xffffffffu, easy)) {
+      float2 xs[25];
 #pragma unroll
-    for (int n1 = 0; n1 < 25; ++n1) {
-      const long long i = base + 16 * n1;
-      float2 xs = make_float2(0.f, 0.f);
-      if (live) {
-        if (vec && i + 1 < n_valid) {
-          xs = __ldg(reinterpret_cast<const float2*>(seg + i));
-        } else {
-          if (i < n_valid) xs.x = __ldg(seg + i);
-          if (i + 1 < n_valid) xs.y = __ldg(seg + i + 1);
-        }
+      for (int n1 = 0; n1 < 25; ++n1) xs[n1] = __ldg(reinterpret_cast<const float2*>(fp + 16 * n1));
+#pragma unroll
+      for (int n1 = 0; n1 < 25; ++n1) {
+        const float2 ws = *reinterpret_cast<const float2*>(&s.w[16 * n1 + 2 * n2]);
+        v[n1] = cmake(xs[n1].x * ws.x, xs[n1].y * ws.y);
       }
-      const float2 ws = *reinterpret_cast<const float2*>(&s.w[16 * n1 + 2 * n2]);
-      v[n1] = cmake(xs.x * ws.x, xs.y * ws.y);
+    } else {
+      const bool vec = (reinterpret_cast<uintptr_t>(fp) & 7) == 0;
+#pragma unroll
+      for (int n1 = 0; n1 < 25; ++n1) {
+        const long long i = base + 16 * n1;
+        float2 xs = make_float2(0.f, 0.f);
+        if (live) {
+          if (vec && i + 1 < n_valid) {
+            xs = __ldg(reinterpret_cast<const float2*>(seg + i));
+          } else {
+            if (i < n_valid) xs.x = __ldg(seg + i);
+            if (i + 1 < n_valid) xs.y = __ldg(seg + i + 1);
+          }
+        }
+        const float2 ws = *reinterpret_cast<const float2*>(&s.w[16 * n1 + 2 * n2]);
+        v[n1] = cmake(xs.x * ws.x, xs.y * ws.y);
+      }
     }
     dft25(v, reinterpret_cast<const cf*>(c_tw25));
     float2* zrow = z + fl * ZS + n2 * 25;
@@ -245,28 +260,34 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   float lmax = -INFINITY;
   float* out = p.logmel + (row0 + wf0) * m;
   if (fb_smem) {
-    // pairs walked without a division per item; weights and spans from shared memory; log10 = log2 * log10(2)
-    // (MUFU.LG2: absolute error ~1e-7 on values of order 1-10, three orders below the 1e-4 gate)
-    int ff = lane / m, j = lane - ff * m;
-    const int df = 32 / m, dj = 32 - df * m;
-    for (int idx = lane; idx < wnf * m; idx += 32) {
-      const int len = s.fb_len[j];
-      const float* fr = &s.fbw[s.fb_off[j]];
-      const float* pf = slab + ff * PS + s.fb_lo[j];
-      float e = 0.f;
-      for (int k = 0; k < len; k += 4) {                          // k ascending, f32 (mel.rs:290-295); padding weights are 0
-        const float4 w4 = *reinterpret_cast<const float4*>(fr + k);
-        e += w4.x * pf[k];
-        e += w4.y * pf[k + 1];
-        e += w4.z * pf[k + 2];
-        e += w4.w * pf[k + 3];
+    // lane = mel row j (j = lane, lane + 32, ...), inner loop over the warp's 4 frames: the span metadata and every 16-byte group of
+    // weights are loaded once per 4 outputs, the power bins with aligned 16-byte loads (spans are widened to 4-aligned bounds with
+    // zero weights, bins 201..203 are zero).  k ascending per output, f32, as the reference (mel.rs:290-295); log10 = log2 * log10(2)
+    // (MUFU.LG2: absolute error ~1e-7 on values of order 1-10, three orders below the 1e-4 gate).
+    for (int j = lane; j < m; j += 32) {
+      const int len = s.fb_len[j], lo = s.fb_lo[j];
+      const float4* fr = reinterpret_cast<const float4*>(&s.fbw[s.fb_off[j]]);
+      const float* pf = slab + lo;
+      float e[FW] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < len; k += 4) {
+        const float4 w4 = fr[k >> 2];
+#pragma unroll
+        for (int ff = 0; ff < FW; ++ff) {
+          const float4 p4 = *reinterpret_cast<const float4*>(pf + ff * PS + k);
+          e[ff] += w4.x * p4.x;
+          e[ff] += w4.y * p4.y;
+          e[ff] += w4.z * p4.z;
+          e[ff] += w4.w * p4.w;
+        }
       }
-      const float v = __log2f(fmaxf(e, 1e-10f)) * 0.30102999566398120f;
-      out[idx] = v;
-      lmax = fmaxf(lmax, v);
-      ff += df;
-      j += dj;
-      if (j >= m) { j -= m; ++ff; }
+#pragma unroll
+      for (int ff = 0; ff < FW; ++ff) {
+        if (ff < wnf) {
+          const float v = __log2f(fmaxf(e[ff], 1e-10f)) * 0.30102999566398120f;
+          out[ff * m + j] = v;
+          lmax = fmaxf(lmax, v);
+        }
+      }
     }
   } else {
     for (int idx = lane; idx < wnf * m; idx += 32) {

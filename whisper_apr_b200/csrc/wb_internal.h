@@ -123,10 +123,14 @@ struct MelTables {                 // device-resident, built at model load
   const int* span_lo;              // [n_mels] first non-zero bin
   const int* span_len;             // [n_mels] bins from first to last non-zero (0 if all-zero row)
   int n_mels;
-  // the same spans packed back to back (row j at packed[span_off[j] .. + span_len[j])): small enough for shared memory when the
-  // bank is triangular (391 weights for slaney-80, ~500 for slaney-128); nullptr when it is not (nnz > 2048 or n_mels > 256)
+  // the same spans packed back to back for shared memory, ALIGNED: row j covers bins [packed_lo[j], packed_lo[j] + packed_len[j])
+  // with packed_lo and packed_len multiples of 4 (zero weights in front of and behind the real span), stored at
+  // packed[span_off[j] ..]: weights and power bins are both read with 16-byte loads.  Triangular banks need ~0.9 k (slaney-80) to
+  // ~1.4 k (slaney-128) weights; nullptr when the bank does not fit (nnz > 2048 or n_mels > 256) -> dense rows from global memory.
   const float* packed;
   const int* span_off;
+  const int* packed_lo;
+  const int* packed_len;
   int nnz;
 };
 // What one mel launch processes.  Regular form: B segments at `audio + b * audio_stride`, n_frames frames each, log-mel rows
