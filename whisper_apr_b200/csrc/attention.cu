@@ -68,6 +68,10 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 // a run-time loop over 32-column chunks re-read from TMEM with the pack/sum one iteration behind the exponentials (0.60).
 // a streaming block (exponentials against the previous blocks' reference max, chunk by chunk under the tcgen05.ld of the next chunk,
 // no token, deferred O rescale) was correct and 5 % slower (0.553).
+// Handing the token over EARLY (after 48 / 32 / 16 of the 64 pairs, so that the other warpgroup's exponentials start under the tail of
+// this one's; token as an mbarrier whose arrival the later pairs depend on, placement checked in the SASS) is slower the larger the
+// overlap: 0.531 / 0.546 / 0.595 against 0.499 with exclusive phases and 0.599 with no token at all (profiles/r02l_attn_handover.txt):
+// two warps of one scheduler inside the MUFU phase at the same time cost more than the hand-over they hide.
 // ptxas also hoists register-only work above the token's bar.sync; pinning the phase behind a post-barrier shared-memory load
 // made it slower (0.549), and made the two-warpgroups-per-tile variant 0.62 instead of 0.73 -- still behind this form.
 // Where the time is (measured): with every tcgen05.mma skipped the kernel takes 0.460 ms, i.e. the softmax + synchronisation

@@ -75,6 +75,7 @@ struct MelKParams {
   const int* n_frames_arr;
   const long long* row_off;
   const int2* tiles;
+  int n_tiles, tiles_per_seg;          // total tiles of the launch; regular form: tiles per segment (tile ti = segment ti / tps)
   const float2* tw200_g;
   const float2* tw400_g;
   float* logmel;
@@ -86,22 +87,6 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   MelSmem& s = *reinterpret_cast<MelSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // ---- which tile
-  int b, f0;
-  if (p.tiles) {
-    const int2 t = p.tiles[blockIdx.x];
-    b = t.x;
-    f0 = t.y;
-  } else {
-    b = blockIdx.y;
-    f0 = blockIdx.x * FT;
-  }
-  const int n_frames = p.n_frames_arr ? p.n_frames_arr[b] : p.n_frames;
-  const int n_valid = p.n_valid ? p.n_valid[b] : p.n_valid_all;
-  const float* seg = p.audio + (p.seg_off ? p.seg_off[b] : static_cast<long long>(b) * p.audio_stride);
-  const long long row0 = p.row_off ? p.row_off[b] : static_cast<long long>(b) * p.n_frames;
-  const int hop = p.hop;
 
   // ---- tables (once per CTA)
   for (int i = tid; i < NFFT; i += MEL_THREADS) s.w[i] = tab.window[i];
@@ -118,14 +103,31 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   }
   __syncthreads();                     // the only CTA-wide barrier
 
+  // ---- persistent CTA: the tables above are loaded once, then the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
   const int fl = lane >> 3, n2 = lane & 7;
-  const int wf0 = f0 + warp * FW;                        // first frame of the warp
-  const int wnf = min(FW, n_frames - wf0);               // live frames of the warp
-  if (wnf <= 0) return;
-  const int f = wf0 + fl;                                // this lane group's frame
-  const bool live = fl < wnf;
+  const int hop = p.hop;
+  const int m = tab.n_mels;
   float* slab = s.slab[warp];
   float2* z = reinterpret_cast<float2*>(slab);
+  for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
+  int b, f0;
+  if (p.tiles) {
+    const int2 t = p.tiles[ti];
+    b = t.x;
+    f0 = t.y;
+  } else {
+    b = ti / p.tiles_per_seg;
+    f0 = (ti - b * p.tiles_per_seg) * FT;
+  }
+  const int n_frames = p.n_frames_arr ? p.n_frames_arr[b] : p.n_frames;
+  const int n_valid = p.n_valid ? p.n_valid[b] : p.n_valid_all;
+  const float* seg = p.audio + (p.seg_off ? p.seg_off[b] : static_cast<long long>(b) * p.audio_stride);
+  const long long row0 = p.row_off ? p.row_off[b] : static_cast<long long>(b) * p.n_frames;
+  const int wf0 = f0 + warp * FW;                        // first frame of the warp
+  const int wnf = min(FW, n_frames - wf0);               // live frames of the warp
+  if (wnf <= 0) continue;
+  const int f = wf0 + fl;                                // this lane group's frame
+  const bool live = fl < wnf;
 
   // ---- load + window + step A: 25-point DFT over n1 of z[8*n1 + n2], then W200^(n2*k1)
   {
@@ -256,7 +258,6 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   __syncwarp();
 
   // ---- filterbank over non-zero spans, log10, store, running max: (frame, mel) pairs of the warp's frames over its 32 lanes
-  const int m = tab.n_mels;
   float lmax = -INFINITY;
   float* out = p.logmel + (row0 + wf0) * m;
   if (fb_smem) {
@@ -305,6 +306,8 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
   if (lane == 0) atomicMax(p.max_key + b, max_key(lmax));          // one atomic per warp
+  __syncwarp();                        // the next tile's z rows overwrite the power rows this warp has just read
+  }
 }
 
 __global__ void mel_init_max_kernel(int* keys, int B) {
@@ -439,14 +442,19 @@ int launch_mel_stft(const MelBatch& job, const MelTables& t, float* logmel, int*
   p.audio = job.audio; p.audio_stride = job.audio_stride; p.seg_off = job.seg_off; p.n_valid = job.n_valid; p.n_valid_all = job.n_valid_all;
   p.hop = job.hop; p.n_frames = job.n_frames; p.n_frames_arr = job.n_frames_arr; p.row_off = job.row_off; p.tiles = job.tiles;
   p.tw200_g = g_tw200[dev]; p.tw400_g = g_tw400[dev]; p.logmel = logmel; p.max_key = chunk_max_key;
-  dim3 grid;
   if (job.tiles) {
     if (job.n_tiles <= 0) return WB_OK;
-    grid = dim3(job.n_tiles, 1);
+    p.n_tiles = job.n_tiles;
+    p.tiles_per_seg = 0;
   } else {
     if (job.n_frames <= 0) return WB_OK;
-    grid = dim3((job.n_frames + FT - 1) / FT, job.B);
+    p.tiles_per_seg = (job.n_frames + FT - 1) / FT;
+    p.n_tiles = p.tiles_per_seg * job.B;
   }
+  // persistent: 3 resident CTAs per SM (launch bounds), each walks ceil(n_tiles / grid) tiles with the tables loaded once
+  const int resident = device_sm_count() * 3;
+  const int per_cta = (p.n_tiles + resident - 1) / resident;
+  const int grid = (p.n_tiles + per_cta - 1) / per_cta;
   mel_stft_kernel<<<grid, MEL_THREADS, sizeof(MelSmem), stream>>>(p, t);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
