@@ -6,7 +6,13 @@
 // 200-point complex DFT is taken with the factorisation 200 = 8 x 25
 // (25 = 5 x 5, radix-5 butterflies in registers), and the real spectrum is
 // recovered with the usual even/odd split.  Every function is host+device so the
-// index algebra is unit-tested on the CPU (tests/test_fft_math.py).
+// index algebra is unit-tested on the CPU (tests/test_abi.py).
+//
+// Device code path: every complex operation is ONE packed fp32x2 instruction (Blackwell's FADD2 / FMUL2 / FFMA2 on a 64-bit register
+// pair; ptxas folds the component swaps, per-half negations and scalar broadcasts of -i, conj and real scales into operand
+// modifiers).  The packed forms run at half the scalar instruction rate (profiles/r02m_f32x2.txt: same flops per clock), so the FP
+// pipe time is unchanged -- what they halve is the ISSUE SLOTS, and the mel kernel is issue-bound (profiles/r02o: issue-active 68 %,
+// FP pipe 41 %).  The rounding of every result is the scalar one (FFMA2 is two independent fused multiply-adds).
 #pragma once
 #include <math.h>
 
@@ -18,13 +24,61 @@
 
 namespace wb {
 
-struct cf { float x, y; };
+struct __attribute__((aligned(8))) cf { float x, y; };
 
 WB_HD cf cmake(float a, float b) { cf r; r.x = a; r.y = b; return r; }
-WB_HD cf cadd(cf a, cf b) { return cmake(a.x + b.x, a.y + b.y); }
-WB_HD cf csub(cf a, cf b) { return cmake(a.x - b.x, a.y - b.y); }
-WB_HD cf cmul(cf a, cf b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-WB_HD cf cscale(cf a, float s) { return cmake(a.x * s, a.y * s); }
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float2 cf2(cf a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ cf f2c(float2 a) { return cmake(a.x, a.y); }
+#endif
+
+WB_HD cf cadd(cf a, cf b) {
+#if defined(__CUDA_ARCH__)
+  return f2c(__fadd2_rn(cf2(a), cf2(b)));
+#else
+  return cmake(a.x + b.x, a.y + b.y);
+#endif
+}
+WB_HD cf csub(cf a, cf b) {
+#if defined(__CUDA_ARCH__)
+  return f2c(__fadd2_rn(cf2(a), make_float2(-b.x, -b.y)));
+#else
+  return cmake(a.x - b.x, a.y - b.y);
+#endif
+}
+// a * b: (a.x b.x - a.y b.y, a.x b.y + a.y b.x) as a multiply and a fused multiply-add per component
+WB_HD cf cmul(cf a, cf b) {
+#if defined(__CUDA_ARCH__)
+  const float2 t = __fmul2_rn(make_float2(a.x, a.x), cf2(b));
+  return f2c(__ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), t));
+#else
+  return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
+}
+// component-wise product (a.x b.x, a.y b.y): two real samples times two window values
+WB_HD cf cmulc(cf a, cf b) {
+#if defined(__CUDA_ARCH__)
+  return f2c(__fmul2_rn(cf2(a), cf2(b)));
+#else
+  return cmake(a.x * b.x, a.y * b.y);
+#endif
+}
+WB_HD cf cscale(cf a, float s) {
+#if defined(__CUDA_ARCH__)
+  return f2c(__fmul2_rn(cf2(a), make_float2(s, s)));
+#else
+  return cmake(a.x * s, a.y * s);
+#endif
+}
+// a + s * b (s real)
+WB_HD cf caxpy(float s, cf b, cf a) {
+#if defined(__CUDA_ARCH__)
+  return f2c(__ffma2_rn(make_float2(s, s), cf2(b), cf2(a)));
+#else
+  return cmake(a.x + s * b.x, a.y + s * b.y);
+#endif
+}
 WB_HD cf cmul_negi(cf a) { return cmake(a.y, -a.x); }   // a * (-i)
 WB_HD cf cconj(cf a) { return cmake(a.x, -a.y); }
 
@@ -32,11 +86,11 @@ WB_HD cf cconj(cf a) { return cmake(a.x, -a.y); }
 WB_HD void dft5(cf& x0, cf& x1, cf& x2, cf& x3, cf& x4) {
   const float c1 = 0.30901699437494745f, c2 = -0.80901699437494745f;
   const float s1 = 0.95105651629515353f, s2 = 0.58778525229247314f;
-  cf t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
-  cf a1 = cmake(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
-  cf a2 = cmake(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
-  cf b1 = cmul_negi(cmake(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
-  cf b2 = cmul_negi(cmake(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+  const cf t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+  const cf a1 = caxpy(c2, t2, caxpy(c1, t1, x0));
+  const cf a2 = caxpy(c1, t2, caxpy(c2, t1, x0));
+  const cf b1 = cmul_negi(caxpy(s2, t4, cscale(t3, s1)));
+  const cf b2 = cmul_negi(caxpy(-s1, t4, cscale(t3, s2)));
   x0 = cadd(x0, cadd(t1, t2));
   x1 = cadd(a1, b1);
   x4 = csub(a1, b1);
@@ -74,16 +128,16 @@ WB_HD void dft25(cf (&v)[25], const cf* __restrict__ tw25) {
 WB_HD void dft8(cf (&v)[8]) {
   const float h = 0.70710678118654752f;
   // radix-2 decimation in time on even/odd
-  cf e0 = cadd(v[0], v[4]), e1 = csub(v[0], v[4]);
-  cf e2 = cadd(v[2], v[6]), e3 = cmul_negi(csub(v[2], v[6]));
-  cf E0 = cadd(e0, e2), E2 = csub(e0, e2), E1 = cadd(e1, e3), E3 = csub(e1, e3);   // DFT4 of (v0,v2,v4,v6)
-  cf o0 = cadd(v[1], v[5]), o1 = csub(v[1], v[5]);
-  cf o2 = cadd(v[3], v[7]), o3 = cmul_negi(csub(v[3], v[7]));
-  cf O0 = cadd(o0, o2), O2 = csub(o0, o2), O1 = cadd(o1, o3), O3 = csub(o1, o3);   // DFT4 of (v1,v3,v5,v7)
-  // twiddles W8^k: 1, (1-i)h, -i, (-1-i)h
-  cf T1 = cmake((O1.x + O1.y) * h, (O1.y - O1.x) * h);
-  cf T2 = cmul_negi(O2);
-  cf T3 = cmake((O3.y - O3.x) * h, -(O3.x + O3.y) * h);
+  const cf e0 = cadd(v[0], v[4]), e1 = csub(v[0], v[4]);
+  const cf e2 = cadd(v[2], v[6]), e3 = cmul_negi(csub(v[2], v[6]));
+  const cf E0 = cadd(e0, e2), E2 = csub(e0, e2), E1 = cadd(e1, e3), E3 = csub(e1, e3);   // DFT4 of (v0,v2,v4,v6)
+  const cf o0 = cadd(v[1], v[5]), o1 = csub(v[1], v[5]);
+  const cf o2 = cadd(v[3], v[7]), o3 = cmul_negi(csub(v[3], v[7]));
+  const cf O0 = cadd(o0, o2), O2 = csub(o0, o2), O1 = cadd(o1, o3), O3 = csub(o1, o3);   // DFT4 of (v1,v3,v5,v7)
+  // twiddles W8^k: 1, (1-i)h, -i, (-1-i)h:   O1 (1 - i) h = (O1 + (-i) O1) h,   O3 (-1 - i) h = ((-i) O3 - O3) h
+  const cf T1 = cscale(cadd(O1, cmul_negi(O1)), h);
+  const cf T2 = cmul_negi(O2);
+  const cf T3 = cscale(csub(cmul_negi(O3), O3), h);
   v[0] = cadd(E0, O0); v[4] = csub(E0, O0);
   v[1] = cadd(E1, T1); v[5] = csub(E1, T1);
   v[2] = cadd(E2, T2); v[6] = csub(E2, T2);
@@ -105,12 +159,12 @@ WB_HD float rfft_power(cf zk, cf zm, cf w) {
 //   E = zk + conj zm,  T = w * (-i) * (zk - conj zm);   X[k] = E + T,   X[200-k] = conj(E - T)
 // -- half the arithmetic of two rfft_power calls, which recompute E and T for each partner.
 WB_HD void rfft_power_pair(cf zk, cf zm, cf w, float& pk, float& pm) {
-  const float ex = zk.x + zm.x, ey = zk.y - zm.y;
-  const float dx = zk.x - zm.x, dy = zk.y + zm.y;
-  const float tx = w.x * dy + w.y * dx, ty = w.y * dy - w.x * dx;
-  const float ax = ex + tx, ay = ey + ty, bx = ex - tx, by = ey - ty;
-  pk = ax * ax + ay * ay;
-  pm = bx * bx + by * by;
+  const cf zc = cconj(zm);
+  const cf e = cadd(zk, zc), d = csub(zk, zc);
+  const cf t = cmul(cmul_negi(d), w);               // (d.y w.x + d.x w.y, d.y w.y - d.x w.x)
+  const cf a = cadd(e, t), b = csub(e, t);
+  pk = a.x * a.x + a.y * a.y;
+  pm = b.x * b.x + b.y * b.y;
 }
 
 }  // namespace wb

@@ -262,14 +262,12 @@ int upload_mel_tables(Replica* m, const std::vector<float>& filt, int n_mels, Me
   std::vector<int> off(n_mels, 0);
   std::vector<float> packed;
   std::vector<int> plo(n_mels, 0), plen(n_mels, 0);
-  for (int j = 0; j < n_mels; ++j) {                      // every span widened with zero weights to 4-aligned bin bounds (16 B loads)
-    off[j] = static_cast<int>(packed.size());
+  for (int j = 0; j < n_mels; ++j) {                      // every span padded with zero weights to a multiple of 4 (16 B loads)
+    off[j] = static_cast<int>(packed.size());             // a multiple of 4: every span starts 16-byte aligned
     if (len[j] == 0) continue;
-    plo[j] = lo[j] & ~3;
-    const int hi = (lo[j] + len[j] + 3) & ~3;           // <= 204: the kernel keeps bins 201..203 of every power row at zero
-    plen[j] = hi - plo[j];
-    for (int k = plo[j]; k < hi; ++k)
-      packed.push_back((k >= lo[j] && k < lo[j] + len[j]) ? filt[static_cast<size_t>(j) * N_FREQ + k] : 0.0f);
+    plo[j] = lo[j];
+    plen[j] = (len[j] + 3) & ~3;                          // lo + plen <= 204: the kernel keeps bins 201..203 of every frame at zero
+    for (int k = 0; k < plen[j]; ++k) packed.push_back(k < len[j] ? filt[static_cast<size_t>(j) * N_FREQ + lo[j] + k] : 0.0f);
   }
   if (n_mels <= 256 && packed.size() <= 2048 && !packed.empty()) {
     float* d_packed;

@@ -39,8 +39,8 @@ constexpr int FT = 32;                 // frames per CTA
 constexpr int FW = 4;                  // frames per warp
 constexpr int MEL_THREADS = 256;
 constexpr int ZS = 200;                // complex values per frame in the exchange slab (2*ZS % 32 == 16: see header)
-constexpr int PS = 216;                // floats per frame of the power spectrum inside the slab (PS % 32 == 24)
-constexpr int SLAB_FLOATS = FW * ZS * 2;       // 1600 floats = 6.4 KB per warp; the power rows (4 x 216) alias its front
+
+constexpr int SLAB_FLOATS = FW * ZS * 2;       // 1600 floats = 6.4 KB per warp; the powers ([204 bins][4 frames]) alias its front
 
 __constant__ float2 c_tw25[25];        // exp(-2*pi*i*b*c/25) at [b*5+c]
 
@@ -144,7 +144,7 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
 #pragma unroll
       for (int n1 = 0; n1 < 25; ++n1) {
         const float2 ws = *reinterpret_cast<const float2*>(&s.w[16 * n1 + 2 * n2]);
-        v[n1] = cmake(xs[n1].x * ws.x, xs[n1].y * ws.y);
+        v[n1] = cmulc(cmake(xs[n1].x, xs[n1].y), cmake(ws.x, ws.y));
       }
     } else {
       const bool vec = (reinterpret_cast<uintptr_t>(fp) & 7) == 0;
@@ -161,7 +161,7 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
           }
         }
         const float2 ws = *reinterpret_cast<const float2*>(&s.w[16 * n1 + 2 * n2]);
-        v[n1] = cmake(xs.x * ws.x, xs.y * ws.y);
+        v[n1] = cmulc(cmake(xs.x, xs.y), cmake(ws.x, ws.y));
       }
     }
     dft25(v, reinterpret_cast<const cf*>(c_tw25));
@@ -232,28 +232,30 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   }
   __syncwarp();                        // every lane has read what it needs from z: the power rows may overwrite the slab
   {
-    float* pf = slab + fl * PS;
+    // powers go back as [bin][frame of the warp]: one 16-byte load in the filterbank gives a bin of all 4 frames, and the 32 lanes of a
+    // store instruction (4 frames x 8 columns) hit 32 consecutive words
+    float* pf = slab + fl;
     if (n2 == 0) {
       pf[0] = pw0[0];
-      pf[200] = pw0[8];
+      pf[200 * FW] = pw0[8];
 #pragma unroll
-      for (int k2 = 1; k2 < 8; ++k2) pf[25 * k2] = pw0[k2];
+      for (int k2 = 1; k2 < 8; ++k2) pf[25 * k2 * FW] = pw0[k2];
     } else {
 #pragma unroll
       for (int k2 = 0; k2 < 8; ++k2) {
-        pf[n2 + 25 * k2] = pw0[k2];
-        pf[25 - n2 + 25 * k2] = pw0[8 + k2];
+        pf[(n2 + 25 * k2) * FW] = pw0[k2];
+        pf[(25 - n2 + 25 * k2) * FW] = pw0[8 + k2];
       }
     }
     if (n2 < 5) {
       const int pcol = 8 + n2;
 #pragma unroll
       for (int k2 = 0; k2 < 8; ++k2) {
-        pf[pcol + 25 * k2] = pw1[k2];
-        pf[25 - pcol + 25 * k2] = pw1[8 + k2];
+        pf[(pcol + 25 * k2) * FW] = pw1[k2];
+        pf[(25 - pcol + 25 * k2) * FW] = pw1[8 + k2];
       }
     }
-    if (n2 == 7) { pf[201] = 0.f; pf[202] = 0.f; pf[203] = 0.f; }     // the zero-weighted padding of the last span reads up to 3 floats past bin 200
+    if (n2 == 7) { pf[201 * FW] = 0.f; pf[202 * FW] = 0.f; pf[203 * FW] = 0.f; }     // zero-weighted padding of a span reads up to bin 203
   }
   __syncwarp();
 
@@ -261,26 +263,27 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
   float lmax = -INFINITY;
   float* out = p.logmel + (row0 + wf0) * m;
   if (fb_smem) {
-    // lane = mel row j (j = lane, lane + 32, ...), inner loop over the warp's 4 frames: the span metadata and every 16-byte group of
-    // weights are loaded once per 4 outputs, the power bins with aligned 16-byte loads (spans are widened to 4-aligned bounds with
-    // zero weights, bins 201..203 are zero).  k ascending per output, f32, as the reference (mel.rs:290-295); log10 = log2 * log10(2)
-    // (MUFU.LG2: absolute error ~1e-7 on values of order 1-10, three orders below the 1e-4 gate).
+    // lane = mel row j (j = lane, lane + 32, ...); every weight of the row's non-zero span meets the bin of all 4 frames of the warp:
+    // one 16-byte power load and two packed FMAs per weight, the weights in 16-byte groups (each span starts 16-byte aligned in the
+    // packed table and is padded to a multiple of 4 with zeros; bins 201..203 are zero).  k ascending per output, f32 fused
+    // multiply-adds, as the reference's loop (mel.rs:290-295); log10 = log2 * log10(2) (MUFU.LG2: absolute error ~1e-7 on values of
+    // order 1-10, three orders below the 1e-4 gate).
     for (int j = lane; j < m; j += 32) {
-      const int len = s.fb_len[j], lo = s.fb_lo[j];
+      const int len = s.fb_len[j];
       const float4* fr = reinterpret_cast<const float4*>(&s.fbw[s.fb_off[j]]);
-      const float* pf = slab + lo;
-      float e[FW] = {0.f, 0.f, 0.f, 0.f};
+      const float4* pb = reinterpret_cast<const float4*>(slab) + s.fb_lo[j];
+      cf e01 = cmake(0.f, 0.f), e23 = cmake(0.f, 0.f);
       for (int k = 0; k < len; k += 4) {
         const float4 w4 = fr[k >> 2];
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int ff = 0; ff < FW; ++ff) {
-          const float4 p4 = *reinterpret_cast<const float4*>(pf + ff * PS + k);
-          e[ff] += w4.x * p4.x;
-          e[ff] += w4.y * p4.y;
-          e[ff] += w4.z * p4.z;
-          e[ff] += w4.w * p4.w;
+        for (int u = 0; u < 4; ++u) {
+          const float4 p4 = pb[k + u];
+          e01 = caxpy(wv[u], cmake(p4.x, p4.y), e01);
+          e23 = caxpy(wv[u], cmake(p4.z, p4.w), e23);
         }
       }
+      const float e[FW] = {e01.x, e01.y, e23.x, e23.y};
 #pragma unroll
       for (int ff = 0; ff < FW; ++ff) {
         if (ff < wnf) {
@@ -295,9 +298,9 @@ mel_stft_kernel(const MelKParams p, const MelTables tab) {
       const int ff = idx / m, j = idx - ff * m;
       const int lo = __ldg(tab.span_lo + j), len = __ldg(tab.span_len + j);
       const float* fr = tab.filters + j * NFREQ + lo;
-      const float* pf = slab + ff * PS + lo;
+      const float* pf = slab + lo * FW + ff;
       float e = 0.f;
-      for (int k = 0; k < len; ++k) e += __ldg(fr + k) * pf[k];      // k ascending, f32 (mel.rs:290-295)
+      for (int k = 0; k < len; ++k) e += __ldg(fr + k) * pf[k * FW];      // k ascending, f32 (mel.rs:290-295)
       const float v = log10f(fmaxf(e, 1e-10f));
       out[idx] = v;
       lmax = fmaxf(lmax, v);

@@ -123,10 +123,11 @@ struct MelTables {                 // device-resident, built at model load
   const int* span_lo;              // [n_mels] first non-zero bin
   const int* span_len;             // [n_mels] bins from first to last non-zero (0 if all-zero row)
   int n_mels;
-  // the same spans packed back to back for shared memory, ALIGNED: row j covers bins [packed_lo[j], packed_lo[j] + packed_len[j])
-  // with packed_lo and packed_len multiples of 4 (zero weights in front of and behind the real span), stored at
-  // packed[span_off[j] ..]: weights and power bins are both read with 16-byte loads.  Triangular banks need ~0.9 k (slaney-80) to
-  // ~1.4 k (slaney-128) weights; nullptr when the bank does not fit (nnz > 2048 or n_mels > 256) -> dense rows from global memory.
+  // the same spans packed back to back for shared memory: row j covers bins [packed_lo[j], packed_lo[j] + packed_len[j]) with
+  // packed_lo = span_lo and packed_len = span_len rounded up to a multiple of 4 (zero weights behind the real span; the kernel keeps
+  // power bins 201..203 at zero), stored at packed[span_off[j] ..] with span_off a multiple of 4: weights are read in 16-byte groups.
+  // Triangular banks need ~0.6 k (slaney-80) to ~0.8 k (slaney-128) weights; nullptr when the bank does not fit (nnz > 2048 or
+  // n_mels > 256) -> dense rows from global memory.
   const float* packed;
   const int* span_off;
   const int* packed_lo;
