@@ -327,6 +327,92 @@ def run_streaming(args, model, lib, torch, dist, stream, rank, world, cfg, load_
                                      "micro_batch": args.chunks, "out_dtype": args.out_dtype},
                           "e2e": e2e, "gpu_launches": int(launches), "setup": {"load_s": round(load_s, 2)}}), flush=True)
 
+def run_transcribe(args, model, lib, torch, dist, stream, rank, world, cfg, load_s):
+    """SURVEY section 8(f1), measured: audio -> token ids through wb_transcribe_tokens_batch (mel + encoder + cross K/V + batched greedy
+    loop on the device, encoder states never leave HBM).  value: generated tokens per second over the whole call; the decode share is
+    the call minus an encoder-only pass of the same batch; its roofline is the HBM stream one token step has to read (f32 decoder
+    weights + the op16 cross K/V of every chunk + the self-attention cache)."""
+    import whisper_apr_b200
+    from whisper_apr_b200 import synth
+    chk = whisper_apr_b200._lib.check
+    B = min(args.chunks, 32)
+    d, S, Ld, V = cfg.n_text_state, 1500, cfg.n_text_layer, cfg.n_vocab
+    T = args.max_tokens
+    init = np.array([50258, 50259, 50359, 50363], np.int32)          # <|startoftranscript|><|en|><|transcribe|><|notimestamps|>
+    ROT = 3
+    host_audio = [torch.empty((B, synth.N_SAMPLES_30S), dtype=torch.float32).pin_memory() for _ in range(ROT)]
+    for r in range(ROT):
+        for i in range(B):
+            host_audio[r][i] = torch.from_numpy(synth.synth_audio((rank * ROT + r) * 4 + i)) if i < 4 else torch.roll(host_audio[r][i % 4], 1000 * i) * (0.5 + 0.01 * i)
+    ptrs = [((C.c_void_p * B)(*[h.data_ptr() + i * synth.N_SAMPLES_30S * 4 for i in range(B)]), (C.c_size_t * B)(*[synth.N_SAMPLES_30S] * B)) for h in host_audio]
+    toks = np.empty((B, T), np.int32)
+    lens = np.empty(B, np.int32)
+    host_out = torch.empty((B, S, cfg.n_audio_state), dtype=torch.float32).pin_memory()
+    model.set_max_batch(B)
+
+    def step_transcribe(i):
+        p, ln = ptrs[i % ROT]
+        chk(lib.wb_transcribe_tokens_batch(model._h, p, ln, B, init.ctypes.data_as(C.c_void_p), init.size, T, 1, toks.ctypes.data_as(C.c_void_p),
+                                           lens.ctypes.data_as(C.c_void_p)))
+        return int((lens - init.size).sum()), int(lens.max()) - 1
+
+    def step_encode(i):
+        p, ln = ptrs[i % ROT]
+        chk(lib.wb_mel_encode_batch(model._h, p, ln, B, C.c_void_p(host_out.data_ptr()), 0))
+        return 0, 0
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        n_tok = n_steps = 0
+        for i in range(steps):
+            a, b = fn(i)
+            n_tok += a
+            n_steps += b
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, n_tok, n_steps
+
+    for i in range(max(args.warmup, 3)):
+        step_transcribe(i)
+        step_encode(i)
+    launches0 = lib.wb_launch_count()
+    ms, n_tok, n_steps = timed(step_transcribe, args.steps)
+    launches = lib.wb_launch_count() - launches0
+    ms_enc, _, _ = timed(step_encode, args.steps)
+    ms_dec = max(ms - ms_enc, 1e-3)
+    peaks = load_peaks()
+    # one token step reads: every f32 decoder matrix once (14 d^2 per layer + the V x d vocabulary projection), the op16 cross K/V of all
+    # B chunks (B * S * 2d per layer) and the f32 self-attention cache written so far (ignored: < 1 % at these lengths)
+    step_bytes = 4.0 * (Ld * 14 * d * d + V * d) + 2.0 * Ld * B * S * 2 * d
+    achieved = step_bytes * n_steps / (ms_dec * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({"metric": f"generated tokens/sec, audio -> token ids (mel + encoder + greedy decode), whisper-{args.model}",
+                          "value": world * n_tok / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 token path, " + lib.wb_operand_format().decode() + " encoder and cross K/V", "data": "synthetic",
+                          "config": {"workload": f"SURVEY 8(f1): {B} chunks x 30 s per GPU per step through wb_transcribe_tokens_batch, greedy, max {T} tokens "
+                                                 f"(random-init weights: sequences run until EOT or {T})", "chunks_per_gpu_per_step": B, "max_tokens": T},
+                          "e2e": {"value": world * n_tok / (ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": B * synth.N_SAMPLES_30S * 4,
+                                  "d2h_bytes_per_step": B * T * 4 + B * 4, "note": "the measured call takes HOST audio and returns HOST token ids"},
+                          "decode": {"tokens_per_s": world * n_tok / (ms_dec / 1e3), "token_steps": n_steps, "us_per_token_step": ms_dec * 1e3 / max(n_steps, 1),
+                                     "ms_encode_per_step": ms_enc / args.steps, "ms_decode_per_step": ms_dec / args.steps},
+                          "roofline": {"kernel": "decoder token step (dec_linear / dec_cross_attn weight + K/V stream)", "bound": "hbm", "achieved": achieved,
+                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                                       "algorithmic_bytes_per_launch": step_bytes, "peak_source": peaks["source"]},
+                          "gpu_launches": int(launches), "setup": {"load_s": round(load_s, 2)}}), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -340,7 +426,8 @@ def main():
     ap.add_argument("--out-dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="chunks", choices=["chunks", "streaming"],
+    ap.add_argument("--max-tokens", type=int, default=64, help="--workload transcribe: GreedyDecoder max_tokens (initial tokens included)")
+    ap.add_argument("--workload", default="chunks", choices=["chunks", "streaming", "transcribe"],
                     help="chunks: 30 s chunks (the headline, BASELINE configs[1..3]); streaming: configs[4] -- per GPU `--streams` streams of 9.5 s "
                          "cut into 5 s chunks with 0.5 s overlap, read in place as views (wb_stream_encode_views)")
     ap.add_argument("--streams", type=int, default=64)
@@ -367,7 +454,7 @@ def main():
     B, d, S, m, L = args.chunks, cfg.n_audio_state, 1500, cfg.n_mels, cfg.n_audio_layer
     quant = {"f32": 0, "int8": 2, "int4": 3}[args.quant]
     t0 = time.time()
-    data, _ = synth.random_model_apr(cfg, quant=quant, seed=0)
+    data, _ = synth.random_model_apr(cfg, quant=quant, seed=0, with_decoder=args.workload == "transcribe")
     t1 = time.time()
     model = WhisperApr.load_from_apr(data, device=local_rank)
     load_s = time.time() - t1                # wb_model_from_apr alone: .apr bytes in host memory -> weights resident in HBM
@@ -379,8 +466,8 @@ def main():
     model.set_stream(stream.cuda_stream)
     lib = whisper_apr_b200.lib()
     setup_s = time.time() - t0
-    if args.workload == "streaming":
-        run_streaming(args, model, lib, torch, dist, stream, rank, world, cfg, load_s)
+    if args.workload in ("streaming", "transcribe"):
+        (run_streaming if args.workload == "streaming" else run_transcribe)(args, model, lib, torch, dist, stream, rank, world, cfg, load_s)
         model.close()
         if world > 1:
             dist.destroy_process_group()

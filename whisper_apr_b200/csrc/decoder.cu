@@ -30,6 +30,23 @@ struct DecodeState {
   DevBuf<int> part_idx;
   DevBuf<int> n_finished;      // [1]
   int argmax_blocks = 0;
+  // CUDA graphs of one token step (forward_one + pick + advance: 14 launches per layer, launch-bound for every Whisper size).  The
+  // position is device-resident, so the same graph serves every position; keyed by the step's shape, captured at the second sighting.
+  struct StepGraph {
+    int B, S, T, pick, sup;
+    const float* logits;
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+  };
+  std::vector<StepGraph> graphs;
+  uintptr_t buf_sig = 0;       // changes when a scratch buffer was reallocated: captured launches hold the old pointers
+  void drop_graphs() {
+    for (auto& g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
+  ~DecodeState() { drop_graphs(); }
 };
 
 namespace {
@@ -37,7 +54,6 @@ namespace {
 constexpr int EOT = 50257, SOT = 50258, LANG_BASE = 50259, TRANSLATE = 50358, TRANSCRIBE = 50359;
 constexpr int SPEAKER_TURN = 50360, PREV = 50361, NO_SPEECH = 50362, NO_TIMESTAMPS = 50363, TIMESTAMP_BASE = 50364;
 constexpr int DH = 64;
-constexpr int DEC_KC = 512;      // x columns staged per pass of the token-path linear kernel (64 KB for 32 rows)
 
 // ------------------------------------------------------------------------------------------------------------------
 // x[b] = token_embedding[token_b] + positional_embedding[pos]           (decoder.rs:2147-2154)
@@ -71,14 +87,15 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[BT], int lane) {
 
 // Skinny f32 linear layer for the token path:  y[b][n] (=|+=) act(x[b] . W[n] + bias[n]),  b < B <= 32, W [N][K] row-major
 // (LinearWeights::forward, attention.rs:143-167).  One warp per group of NC output columns: the warp streams NC rows of W once
-// (coalesced float4), every lane keeps BT x NC partial sums, x lives in shared memory.  Bound by the W stream for small B.
+// (coalesced float4, two k-steps in flight), every lane keeps BT x NC partial sums, and x (B x K floats, the same for every warp of
+// the launch) is read through L1 -- the first version staged a [32][512] slice of x in shared memory per block with a scalar,
+// division-indexed copy loop that cost ~29 us per slice (48 dependent L2 round trips), i.e. more than the whole product.
 // MODE 0: store; 1: GELU then store; 2: accumulate into y (residual);  3: logits -> suppression + running argmax (no store unless y)
 template <int BT, int NC, int MODE>
 __global__ void __launch_bounds__(256) dec_linear_kernel(const float* __restrict__ x, int B, int K, const float* __restrict__ W,
                                                          const float* __restrict__ bias, int N, float* __restrict__ y, int ldy,
                                                          const uint8_t* __restrict__ suppress, float* __restrict__ part_val,
                                                          int* __restrict__ part_idx) {
-  extern __shared__ __align__(16) float sx[];                 // [BT][DEC_KC] slice of x
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * NC;         // this warp's NC output columns
   float acc[NC][BT];
@@ -86,33 +103,39 @@ __global__ void __launch_bounds__(256) dec_linear_kernel(const float* __restrict
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[c][b] = 0.f;
-  for (int kc = 0; kc < K; kc += DEC_KC) {
-    const int kn = min(DEC_KC, K - kc);
-    __syncthreads();
-    for (int i = tid; i < BT * kn; i += blockDim.x) {
-      const int b = i / kn, kk = i - b * kn;
-      sx[b * DEC_KC + kk] = b < B ? x[static_cast<size_t>(b) * K + kc + kk] : 0.f;
+  if (n0 < N) {
+    const float4* wrow[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) wrow[c] = reinterpret_cast<const float4*>(W + static_cast<size_t>(min(n0 + c, N - 1)) * K);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int K4 = K >> 2;
+    float4 w[NC], wn[NC];
+    int k4 = lane;
+    if (k4 < K4) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) w[c] = __ldg(wrow[c] + k4);
     }
-    __syncthreads();
-    if (n0 < N) {
-      for (int k4 = lane; k4 < (kn >> 2); k4 += 32) {
-        float4 w[NC];
+    for (; k4 < K4; k4 += 32) {
+      const bool more = k4 + 32 < K4;
+      if (more) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) wn[c] = __ldg(wrow[c] + k4 + 32);      // next k-step's weights are in flight under this one's FMAs
+      }
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        // rows past B repeat row B - 1 (their sums are never stored)
+        const float4 xv = __ldg(x4 + static_cast<size_t>(min(b, B - 1)) * K4 + k4);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const int n = min(n0 + c, N - 1);
-          w[c] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + kc) + k4);
+          acc[c][b] = fmaf(w[c].x, xv.x, acc[c][b]);
+          acc[c][b] = fmaf(w[c].y, xv.y, acc[c][b]);
+          acc[c][b] = fmaf(w[c].z, xv.z, acc[c][b]);
+          acc[c][b] = fmaf(w[c].w, xv.w, acc[c][b]);
         }
+      }
+      if (more) {
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          const float4 xv = reinterpret_cast<const float4*>(sx + b * DEC_KC)[k4];
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            acc[c][b] = fmaf(w[c].x, xv.x, acc[c][b]);
-            acc[c][b] = fmaf(w[c].y, xv.y, acc[c][b]);
-            acc[c][b] = fmaf(w[c].z, xv.z, acc[c][b]);
-            acc[c][b] = fmaf(w[c].w, xv.w, acc[c][b]);
-          }
-        }
+        for (int c = 0; c < NC; ++c) w[c] = wn[c];
       }
     }
   }
@@ -216,33 +239,50 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
 }
 
 // Cross-attention of one query row over the chunk's S cached encoder keys / values (op16 [B*S][2d]: K at column h*64, V at
-// column d + h*64).  One block per (chunk, head), 256 threads.
+// column d + h*64).  One block per (chunk, head), 256 threads.  Both passes over the cache keep several independent 128-byte row
+// loads in flight per warp (the first version walked one key per thread / one row per warp step by step: 98 us per layer for 73 MB).
 __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __restrict__ q, const op16* __restrict__ kv, int S, int d,
                                                              float* __restrict__ out) {
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  extern __shared__ float sm[];                // q[64] | p[S]
-  float* sq = sm;
-  float* sp = sm + DH;
-  if (tid < DH) sq[tid] = q[static_cast<size_t>(b) * d + h * DH + tid];
-  __syncthreads();
+  extern __shared__ float sm[];                // p[S]
+  float* sp = sm;
   const op16* base = kv + static_cast<size_t>(b) * S * 2 * d;
+  // scores: a key's 64-dim row (128 B) is read by 8 lanes, 16 B each; a warp covers 4 keys per step, the block 32
+  const int sub = lane & 7, g = lane >> 3;
+  float qv[8];
+  {
+    const float4* q4 = reinterpret_cast<const float4*>(q + static_cast<size_t>(b) * d + h * DH + sub * 8);
+    const float4 a = __ldg(q4), c = __ldg(q4 + 1);
+    qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = c.x; qv[5] = c.y; qv[6] = c.z; qv[7] = c.w;
+  }
   float lmax = -INFINITY;
-  for (int t = tid; t < S; t += blockDim.x) {
-    const uint4* k8 = reinterpret_cast<const uint4*>(base + static_cast<size_t>(t) * 2 * d + h * DH);
-    float s = 0.f;
+  constexpr int UN = 4;
+  for (int t0 = warp * 4 + g; t0 < S; t0 += 32 * UN) {
+    uint4 u[UN];
 #pragma unroll
-    for (int i = 0; i < DH / 8; ++i) {
-      const uint4 u = __ldg(k8 + i);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int r = 0; r < UN; ++r) {
+      const int t = t0 + 32 * r;
+      u[r] = t < S ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(t) * 2 * d + h * DH) + sub) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < UN; ++r) {
+      const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
+      float sc = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        s = fmaf(unpack_op16_lo(w[j]), sq[8 * i + 2 * j], s);
-        s = fmaf(unpack_op16_hi(w[j]), sq[8 * i + 2 * j + 1], s);
+        sc = fmaf(unpack_op16_lo(w[j]), qv[2 * j], sc);
+        sc = fmaf(unpack_op16_hi(w[j]), qv[2 * j + 1], sc);
+      }
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      sc *= 0.125f;                                // 1 / sqrt(64)
+      const int t = t0 + 32 * r;
+      if (t < S) {
+        if (sub == 0) sp[t] = sc;
+        lmax = fmaxf(lmax, sc);
       }
     }
-    s *= 0.125f;
-    sp[t] = s;
-    lmax = fmaxf(lmax, s);
   }
   __shared__ float red[8];
 #pragma unroll
@@ -267,13 +307,25 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += red[w];
   const float inv = 1.0f / tot;
-  // PV: warp w takes keys w, w + 8, ...; a lane owns two output dims (one coalesced 128 B row of V per step)
+  // PV: warp w takes keys w, w + 8, ...; a lane owns two output dims (one coalesced 128 B row of V per key), 8 rows in flight
   float a0 = 0.f, a1 = 0.f;
-  for (int t = warp; t < S; t += 8) {
-    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(base + static_cast<size_t>(t) * 2 * d + d + h * DH) + lane);
-    const float p = sp[t];
-    a0 = fmaf(p, unpack_op16_lo(u), a0);
-    a1 = fmaf(p, unpack_op16_hi(u), a1);
+  constexpr int UV = 8;
+  const uint32_t* vbase = reinterpret_cast<const uint32_t*>(base + d + h * DH) + lane;
+  const size_t vstride = static_cast<size_t>(d);           // 2d op16 per key = d 32-bit words
+  for (int t0 = warp; t0 < S; t0 += 8 * UV) {
+    uint32_t u[UV];
+#pragma unroll
+    for (int r = 0; r < UV; ++r) {
+      const int t = t0 + 8 * r;
+      u[r] = t < S ? __ldg(vbase + static_cast<size_t>(t) * vstride) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < UV; ++r) {
+      const int t = t0 + 8 * r;
+      const float p = t < S ? sp[t] : 0.f;
+      a0 = fmaf(p, unpack_op16_lo(u[r]), a0);
+      a1 = fmaf(p, unpack_op16_hi(u[r]), a1);
+    }
   }
   __shared__ float part[8][DH];
   part[warp][2 * lane] = a0;
@@ -289,20 +341,32 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
 
 // Reduce the per-block argmax partials, then append the token (greedy.rs:118-146): a chunk that emitted EOT stays finished.
 // step + 1 < n_init: the next token is the prompt's, nothing to pick.
-__global__ void dec_pick_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n_blocks, int B, int T,
+__global__ void __launch_bounds__(1024) dec_pick_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n_blocks, int B, int T,
                                 int* __restrict__ tokens, int* __restrict__ lens, int* __restrict__ finished, int* __restrict__ n_finished,
                                 const int* __restrict__ pos_p) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int pos = *pos_p;
-  if (finished[b]) return;
+  // lane = chunk b, warp w scans partials w, w + 32, ... (a single thread per chunk walked all ~1600 partials of a 51865-token
+  // vocabulary through dependent L2 round trips: 200 us per token); ties resolve to the smaller index at every level
+  const int b = threadIdx.x & 31, w = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  __shared__ float sv[32][32];
+  __shared__ int si[32][32];
   float bv = -INFINITY;
   int bi = 0x7fffffff;
-  for (int k = 0; k < n_blocks; ++k) {
+  for (int k = w; k < n_blocks; k += n_warps) {
     const float v = part_val[k * 32 + b];
     const int i = part_idx[k * 32 + b];
     if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
   }
+  sv[w][b] = bv;
+  si[w][b] = bi;
+  __syncthreads();
+  if (w != 0 || b >= B) return;
+  for (int k = 1; k < n_warps; ++k) {
+    const float v = sv[k][b];
+    const int i = si[k][b];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  const int pos = *pos_p;
+  if (finished[b]) return;
   if (bi == 0x7fffffff) bi = 0;                 // every logit -inf or NaN: argmax returns index 0 (greedy.rs:84-85)
   tokens[b * T + pos + 1] = bi;
   lens[b] = pos + 2;
@@ -331,16 +395,7 @@ int launch_dec_linear(const float* x, int B, int K, const float* W, const float*
   if (blocks_out) *blocks_out = blocks;
   auto go = [&](auto bt) -> int {
     constexpr int BT = decltype(bt)::value;
-    constexpr int SMEM = BT * DEC_KC * 4;
-    if (SMEM > 48 * 1024) {                                  // beyond the default dynamic shared-memory limit: per-device opt-in
-      static PerDeviceOnce once;
-      int rc = once.run([](int) -> int {
-        WB_CUDA_OK(cudaFuncSetAttribute(dec_linear_kernel<BT, NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        return WB_OK;
-      });
-      if (rc != WB_OK) return rc;
-    }
-    dec_linear_kernel<BT, NC, MODE><<<blocks, 256, SMEM, st>>>(x, B, K, W, bias, N, y, ldy, suppress, part_val, part_idx);
+    dec_linear_kernel<BT, NC, MODE><<<blocks, 256, 0, st>>>(x, B, K, W, bias, N, y, ldy, suppress, part_val, part_idx);
     return WB_OK;
   };
   int rc;
@@ -367,6 +422,17 @@ int ensure_decode_state(Replica* m, int B, int S, int T) {
       (rc = s.part_idx.ensure((static_cast<size_t>(w.n_vocab) / 32 + 2) * 32)))
     return rc;
   s.cap_B = B; s.cap_S = S; s.cap_T = T;
+  uintptr_t sig = 0;
+  for (const void* q : {static_cast<const void*>(s.kv_cross.p), static_cast<const void*>(s.kv_self.p), static_cast<const void*>(s.x.p),
+                        static_cast<const void*>(s.xn.p), static_cast<const void*>(s.qkv.p), static_cast<const void*>(s.att.p),
+                        static_cast<const void*>(s.hid.p), static_cast<const void*>(s.q.p), static_cast<const void*>(s.tokens.p),
+                        static_cast<const void*>(s.lens.p), static_cast<const void*>(s.finished.p), static_cast<const void*>(s.pos.p),
+                        static_cast<const void*>(s.n_finished.p), static_cast<const void*>(s.part_val.p), static_cast<const void*>(s.part_idx.p)})
+    sig = sig * 1000003u + reinterpret_cast<uintptr_t>(q);
+  if (sig != s.buf_sig) {
+    s.drop_graphs();
+    s.buf_sig = sig;
+  }
   return WB_OK;
 }
 
@@ -392,7 +458,7 @@ int forward_one(Replica* m, int B, int S, int T, bool want_logits, int suppress_
     if ((rc = launch_layernorm(s.x.p, lw.ln2_g, lw.ln2_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
     if ((rc = launch_dec_linear<0>(s.xn.p, B, d, lw.ca_wq, lw.ca_bq, d, s.q.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     const op16* kv = s.kv_cross.p + static_cast<size_t>(l) * B * S * 2 * d;
-    dec_cross_attn_kernel<<<dim3(B, H), 256, (DH + S) * sizeof(float), st>>>(s.q.p, kv, S, d, s.att.p);
+    dec_cross_attn_kernel<<<dim3(B, H), 256, S * sizeof(float), st>>>(s.q.p, kv, S, d, s.att.p);
     count_launch();
     if ((rc = launch_dec_linear<2>(s.att.p, B, d, lw.ca_wo, lw.ca_bo, d, s.x.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     // FFN
@@ -407,6 +473,66 @@ int forward_one(Replica* m, int B, int S, int T, bool want_logits, int suppress_
       return rc;
   }
   WB_CUDA_OK(cudaGetLastError());
+  return WB_OK;
+}
+
+// One token step for the B rows -- forward_one, the pick of the next token (when this position emits one) and the position advance --
+// replayed from a CUDA graph from its third occurrence on (first: eager, which also runs the per-device kernel attribute set-up;
+// second: captured).  Eager when graphs are disabled (WB_NO_GRAPH) or the per-kernel profile is on.
+int token_step(Replica* m, int B, int S, int T, bool pick, int sup_set, float* d_logits) {
+  DecodeState& s = *m->dstate;
+  cudaStream_t st = m->stream;
+  auto eager = [&]() -> int {
+    int rc = forward_one(m, B, S, T, pick, sup_set, d_logits);
+    if (rc != WB_OK) return rc;
+    if (pick) {
+      dec_pick_kernel<<<1, 1024, 0, st>>>(s.part_val.p, s.part_idx.p, s.argmax_blocks, B, T, s.tokens.p, s.lens.p, s.finished.p,
+                                                     s.n_finished.p, s.pos.p);
+      count_launch();
+    }
+    dec_advance_kernel<<<1, 1, 0, st>>>(s.pos.p);
+    count_launch();
+    return WB_OK;
+  };
+  if (!m->use_graphs || m->prof_on) return eager();
+  DecodeState::StepGraph* g = nullptr;
+  for (auto& e : s.graphs)
+    if (e.B == B && e.S == S && e.T == T && e.pick == static_cast<int>(pick) && e.sup == sup_set && e.logits == d_logits) g = &e;
+  if (!g) {
+    if (s.graphs.size() >= 16) s.drop_graphs();
+    DecodeState::StepGraph e;
+    e.B = B; e.S = S; e.T = T; e.pick = pick; e.sup = sup_set; e.logits = d_logits; e.seen = 1;
+    s.graphs.push_back(e);
+    return eager();
+  }
+  if (g->exec) {
+    WB_CUDA_OK(cudaGraphLaunch(g->exec, st));
+    count_launch(static_cast<int>(g->launches));
+    return WB_OK;
+  }
+  const long long before = g_launch_count.load();
+  WB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = eager();
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != WB_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    m->use_graphs = false;
+    if (rc != WB_OK) return rc;
+    return eager();
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    m->use_graphs = false;
+    return eager();
+  }
+  g->exec = exec;
+  g->launches = g_launch_count.load() - before;
+  WB_CUDA_OK(cudaGraphLaunch(exec, st));
   return WB_OK;
 }
 
@@ -550,14 +676,7 @@ int decoder_greedy_s(Replica* m, const op16* d_states, int B, int S, const int* 
   int h_finished = 0;
   for (int p = 0; p + 1 < T && T > n_init; ++p) {
     const bool pick = p >= n_init - 1;
-    if ((rc = forward_one(m, B, S, T, pick, sup_set, logits_last_host ? d_logits.p : nullptr)) != WB_OK) return rc;
-    if (pick) {
-      dec_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(s.part_val.p, s.part_idx.p, s.argmax_blocks, B, T, s.tokens.p, s.lens.p, s.finished.p,
-                                                     s.n_finished.p, s.pos.p);
-      count_launch();
-    }
-    dec_advance_kernel<<<1, 1, 0, st>>>(s.pos.p);
-    count_launch();
+    if ((rc = token_step(m, B, S, T, pick, sup_set, logits_last_host ? d_logits.p : nullptr)) != WB_OK) return rc;
     if (pick && ((p - n_init + 2) % 16 == 0)) {              // every 16 generated tokens: has every chunk emitted EOT?
       WB_CUDA_OK(cudaMemcpyAsync(&h_finished, s.n_finished.p, sizeof(int), cudaMemcpyDeviceToHost, st));
       WB_CUDA_OK(cudaStreamSynchronize(st));
