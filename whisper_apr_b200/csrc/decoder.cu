@@ -26,10 +26,9 @@ struct DecodeState {
   DevBuf<float> x, xn, qkv, att, hid, q, logits;
   DevBuf<int> tokens;          // [B][T]
   DevBuf<int> lens, finished, pos;     // [B], [B], [1]
-  DevBuf<float> part_val;      // [blocks][B]
-  DevBuf<int> part_idx;
+  DevBuf<unsigned long long> part_key;   // [argmax groups][32]: packed (ordered logit, ~token id) maxima, zero = "nothing yet"
   DevBuf<int> n_finished;      // [1]
-  int argmax_blocks = 0;
+  int argmax_groups = 0;
   // CUDA graphs of one token step (forward_one + pick + advance: 14 launches per layer, launch-bound for every Whisper size).  The
   // position is device-resident, so the same graph serves every position; keyed by the step's shape, captured at the second sighting.
   struct StepGraph {
@@ -86,45 +85,58 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[BT], int lane) {
 }
 
 // Skinny f32 linear layer for the token path:  y[b][n] (=|+=) act(x[b] . W[n] + bias[n]),  b < B <= 32, W [N][K] row-major
-// (LinearWeights::forward, attention.rs:143-167).  One warp per group of NC output columns: the warp streams NC rows of W once
-// (coalesced float4, two k-steps in flight), every lane keeps BT x NC partial sums, and x (B x K floats, the same for every warp of
-// the launch) is read through L1 -- the first version staged a [32][512] slice of x in shared memory per block with a scalar,
-// division-indexed copy loop that cost ~29 us per slice (48 dependent L2 round trips), i.e. more than the whole product.
-// MODE 0: store; 1: GELU then store; 2: accumulate into y (residual);  3: logits -> suppression + running argmax (no store unless y)
+// (LinearWeights::forward, attention.rs:143-167).  One BLOCK per group of NC output columns, its threads split K: thread t owns the
+// float4 columns t, t + blockDim, ... of the NC weight rows (coalesced, the next step's weights in flight under this one's FMAs) and
+// keeps BT x NC partial sums; x (B x K floats, the same for every block) is read through L1.  Partial sums meet in a warp
+// reduce-scatter, then across the warps through shared memory in a fixed order (deterministic).  Decoder matrices are small (d x d
+// is 0.6 MB for tiny): splitting K over the block instead of giving a warp the whole row turns 3-12 dependent k-steps into 1-2 and
+// spreads a d x d product over d / 4 blocks instead of d / 32.
+// History: v1 staged a [32][512] slice of x in shared memory with a scalar, division-indexed copy loop (29 us per slice: 48 dependent
+// L2 round trips); v2 (one warp per NC columns over all of K) 12 us for d x d, 26 us for 4d x d.
+// MODE 0: store; 1: GELU then store; 2: accumulate into y (residual);  3: logits -> suppression -> packed running argmax (stores y if given)
+constexpr int PICK_GROUP = 64;        // MODE 3: this many consecutive blocks share one row of packed argmax keys
+
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+  // order-preserving float -> unsigned, token id complemented: the maximum key is the largest logit, ties -> the SMALLEST id, which is
+  // GreedyDecoder::argmax's first strict maximum (greedy.rs:83-96)
+  const uint32_t u = __float_as_uint(v);
+  const uint32_t ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (static_cast<unsigned long long>(ord) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(idx));
+}
+
 template <int BT, int NC, int MODE>
 __global__ void __launch_bounds__(256) dec_linear_kernel(const float* __restrict__ x, int B, int K, const float* __restrict__ W,
                                                          const float* __restrict__ bias, int N, float* __restrict__ y, int ldy,
-                                                         const uint8_t* __restrict__ suppress, float* __restrict__ part_val,
-                                                         int* __restrict__ part_idx) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * NC;         // this warp's NC output columns
+                                                         const uint8_t* __restrict__ suppress, unsigned long long* __restrict__ part_key) {
+  __shared__ float part[8][NC][BT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nw = NT >> 5;
+  const int n0 = blockIdx.x * NC;
   float acc[NC][BT];
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[c][b] = 0.f;
-  if (n0 < N) {
+  {
     const float4* wrow[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) wrow[c] = reinterpret_cast<const float4*>(W + static_cast<size_t>(min(n0 + c, N - 1)) * K);
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const int K4 = K >> 2;
     float4 w[NC], wn[NC];
-    int k4 = lane;
+    int k4 = tid;
     if (k4 < K4) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) w[c] = __ldg(wrow[c] + k4);
     }
-    for (; k4 < K4; k4 += 32) {
-      const bool more = k4 + 32 < K4;
+    for (; k4 < K4; k4 += NT) {
+      const bool more = k4 + NT < K4;
       if (more) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) wn[c] = __ldg(wrow[c] + k4 + 32);      // next k-step's weights are in flight under this one's FMAs
+        for (int c = 0; c < NC; ++c) wn[c] = __ldg(wrow[c] + k4 + NT);
       }
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
-        // rows past B repeat row B - 1 (their sums are never stored)
-        const float4 xv = __ldg(x4 + static_cast<size_t>(min(b, B - 1)) * K4 + k4);
+        const float4 xv = __ldg(x4 + static_cast<size_t>(min(b, B - 1)) * K4 + k4);      // rows past B repeat row B - 1 (never stored)
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           acc[c][b] = fmaf(w[c].x, xv.x, acc[c][b]);
@@ -139,43 +151,26 @@ __global__ void __launch_bounds__(256) dec_linear_kernel(const float* __restrict
       }
     }
   }
-  float best_v = -INFINITY;
-  int best_i = 0x7fffffff;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    const int n = n0 + c;
-    float r = warp_reduce_scatter<BT>(acc[c], lane);         // lane l: total for row b = l % BT
-    const int b = lane % BT;
-    if (n < N && b < B && lane < BT) {
-      r += bias ? bias[n] : 0.f;
-      if (MODE == 1) r = gelu_tanh(r);
-      if (MODE == 2) y[static_cast<size_t>(b) * ldy + n] += r;
-      else if (MODE == 3) {
-        if (y) y[static_cast<size_t>(b) * ldy + n] = r;
-        const float sl = suppress[n] ? -INFINITY : r;          // WhisperTokenSuppressor::apply (processors.rs:126-147)
-        if (sl > best_v) { best_v = sl; best_i = n; }          // ascending n: strict > keeps the first maximum
-      } else {
-        y[static_cast<size_t>(b) * ldy + n] = r;
-      }
-    }
+    const float r = warp_reduce_scatter<BT>(acc[c], lane);   // lane l: this warp's total for row l % BT
+    if (lane < BT) part[warp][c][lane] = r;
   }
-  if (MODE == 3) {
-    // block-level argmax per row: first maximum wins (greedy.rs:83-96) = larger value, or equal value and smaller index
-    __shared__ float sv[8][32];
-    __shared__ int si[8][32];
-    sv[warp][lane] = best_v;
-    si[warp][lane] = best_i;
-    __syncthreads();
-    if (warp == 0 && lane < BT && lane < B) {
-      float bv = sv[0][lane];
-      int bi = si[0][lane];
-      for (int w = 1; w < (blockDim.x >> 5); ++w) {
-        const float v = sv[w][lane];
-        const int i = si[w][lane];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-      }
-      part_val[blockIdx.x * 32 + lane] = bv;
-      part_idx[blockIdx.x * 32 + lane] = bi;
+  __syncthreads();
+  for (int i = tid; i < NC * BT; i += NT) {
+    const int c = i / BT, b = i - c * BT, n = n0 + c;
+    if (n >= N || b >= B) continue;
+    float r = part[0][c][b];
+    for (int w = 1; w < nw; ++w) r += part[w][c][b];
+    r += bias ? bias[n] : 0.f;
+    if (MODE == 1) r = gelu_tanh(r);
+    if (MODE == 2) y[static_cast<size_t>(b) * ldy + n] += r;
+    else if (MODE == 3) {
+      if (y) y[static_cast<size_t>(b) * ldy + n] = r;
+      // WhisperTokenSuppressor::apply (processors.rs:126-147): suppressed ids never win; neither do -inf / NaN logits
+      if (!suppress[n] && r > -INFINITY) atomicMax(part_key + (blockIdx.x / PICK_GROUP) * 32 + b, argmax_key(r, n));
+    } else {
+      y[static_cast<size_t>(b) * ldy + n] = r;
     }
   }
 }
@@ -256,7 +251,7 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
     qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = c.x; qv[5] = c.y; qv[6] = c.z; qv[7] = c.w;
   }
   float lmax = -INFINITY;
-  constexpr int UN = 4;
+  constexpr int UN = 8;
   for (int t0 = warp * 4 + g; t0 < S; t0 += 32 * UN) {
     uint4 u[UN];
 #pragma unroll
@@ -307,9 +302,9 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += red[w];
   const float inv = 1.0f / tot;
-  // PV: warp w takes keys w, w + 8, ...; a lane owns two output dims (one coalesced 128 B row of V per key), 8 rows in flight
+  // PV: warp w takes keys w, w + 8, ...; a lane owns two output dims (one coalesced 128 B row of V per key), 16 rows in flight
   float a0 = 0.f, a1 = 0.f;
-  constexpr int UV = 8;
+  constexpr int UV = 16;
   const uint32_t* vbase = reinterpret_cast<const uint32_t*>(base + d + h * DH) + lane;
   const size_t vstride = static_cast<size_t>(d);           // 2d op16 per key = d 32-bit words
   for (int t0 = warp; t0 < S; t0 += 8 * UV) {
@@ -341,33 +336,26 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
 
 // Reduce the per-block argmax partials, then append the token (greedy.rs:118-146): a chunk that emitted EOT stays finished.
 // step + 1 < n_init: the next token is the prompt's, nothing to pick.
-__global__ void __launch_bounds__(1024) dec_pick_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n_blocks, int B, int T,
+__global__ void __launch_bounds__(1024) dec_pick_kernel(unsigned long long* __restrict__ part_key, int n_groups, int B, int T,
                                 int* __restrict__ tokens, int* __restrict__ lens, int* __restrict__ finished, int* __restrict__ n_finished,
                                 const int* __restrict__ pos_p) {
-  // lane = chunk b, warp w scans partials w, w + 32, ... (a single thread per chunk walked all ~1600 partials of a 51865-token
-  // vocabulary through dependent L2 round trips: 200 us per token); ties resolve to the smaller index at every level
+  // lane = chunk b, warp w scans key rows w, w + 32, ... and clears them for the next position
   const int b = threadIdx.x & 31, w = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  __shared__ float sv[32][32];
-  __shared__ int si[32][32];
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int k = w; k < n_blocks; k += n_warps) {
-    const float v = part_val[k * 32 + b];
-    const int i = part_idx[k * 32 + b];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  __shared__ unsigned long long sk[32][32];
+  unsigned long long best = 0ull;
+  for (int k = w; k < n_groups; k += n_warps) {
+    const unsigned long long v = part_key[k * 32 + b];
+    part_key[k * 32 + b] = 0ull;
+    best = v > best ? v : best;
   }
-  sv[w][b] = bv;
-  si[w][b] = bi;
+  sk[w][b] = best;
   __syncthreads();
   if (w != 0 || b >= B) return;
-  for (int k = 1; k < n_warps; ++k) {
-    const float v = sv[k][b];
-    const int i = si[k][b];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-  }
+  for (int k = 1; k < n_warps; ++k) best = sk[k][b] > best ? sk[k][b] : best;
   const int pos = *pos_p;
   if (finished[b]) return;
-  if (bi == 0x7fffffff) bi = 0;                 // every logit -inf or NaN: argmax returns index 0 (greedy.rs:84-85)
+  // no key at all: every logit was -inf, NaN or suppressed -> argmax returns index 0 (greedy.rs:84-85)
+  const int bi = best == 0ull ? 0 : static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(best & 0xFFFFFFFFull));
   tokens[b * T + pos + 1] = bi;
   lens[b] = pos + 2;
   if (bi == EOT) {
@@ -376,8 +364,10 @@ __global__ void __launch_bounds__(1024) dec_pick_kernel(const float* __restrict_
   }
 }
 __global__ void dec_advance_kernel(int* pos_p) { *pos_p += 1; }
-__global__ void dec_init_kernel(int* tokens, int T, int B, const int* init, int n_init, int* lens, int* finished, int* pos, int* n_finished) {
+__global__ void dec_init_kernel(int* tokens, int T, int B, const int* init, int n_init, int* lens, int* finished, int* pos, int* n_finished,
+                                unsigned long long* part_key, int n_keys) {
   const int b = blockIdx.x;
+  for (int i = b * blockDim.x + threadIdx.x; i < n_keys; i += gridDim.x * blockDim.x) part_key[i] = 0ull;   // a logits-only call may have left keys
   for (int i = threadIdx.x; i < T; i += blockDim.x) tokens[b * T + i] = i < n_init ? init[i] : EOT;
   if (threadIdx.x == 0) {
     lens[b] = n_init;
@@ -388,14 +378,17 @@ __global__ void dec_init_kernel(int* tokens, int T, int B, const int* init, int 
 
 template <int MODE>
 int launch_dec_linear(const float* x, int B, int K, const float* W, const float* bias, int N, float* y, int ldy, const uint8_t* suppress,
-                      float* part_val, int* part_idx, int* blocks_out, cudaStream_t st) {
+                      unsigned long long* part_key, int* groups_out, cudaStream_t st) {
   if (K % 4 != 0) return set_error(WB_ERR_MODEL, "decoder width must be a multiple of 4");
   constexpr int NC = 4;
-  const int blocks = ((N + NC - 1) / NC + 7) / 8;             // one warp per NC columns, 8 warps per block
-  if (blocks_out) *blocks_out = blocks;
+  const int blocks = (N + NC - 1) / NC;                       // one block per NC columns; its threads split K
+  // small matrices: split K over the whole block (1-2 k-steps per thread, d / 4 blocks).  The vocabulary projection has blocks to spare
+  // (13 k for 51865 tokens), and there the cross-warp reduction costs more than it saves (168 us against 120 us): one warp per block.
+  const int threads = blocks >= 4096 ? 32 : std::min(256, std::max(32, ((K / 4 + 31) / 32) * 32));
+  if (groups_out) *groups_out = (blocks + PICK_GROUP - 1) / PICK_GROUP;
   auto go = [&](auto bt) -> int {
     constexpr int BT = decltype(bt)::value;
-    dec_linear_kernel<BT, NC, MODE><<<blocks, 256, 0, st>>>(x, B, K, W, bias, N, y, ldy, suppress, part_val, part_idx);
+    dec_linear_kernel<BT, NC, MODE><<<blocks, threads, 0, st>>>(x, B, K, W, bias, N, y, ldy, suppress, part_key);
     return WB_OK;
   };
   int rc;
@@ -409,6 +402,9 @@ int launch_dec_linear(const float* x, int B, int K, const float* W, const float*
   return WB_OK;
 }
 
+// rows of packed argmax keys the vocabulary projection needs (one per PICK_GROUP blocks of 4 columns)
+static size_t key_rows(int n_vocab) { return (static_cast<size_t>(n_vocab) / 4 + PICK_GROUP) / PICK_GROUP + 1; }
+
 int ensure_decode_state(Replica* m, int B, int S, int T) {
   if (!m->dstate) m->dstate = new DecodeState();
   DecodeState& s = *m->dstate;
@@ -418,8 +414,7 @@ int ensure_decode_state(Replica* m, int B, int S, int T) {
   if ((rc = s.kv_cross.ensure(L * b * S * 2 * d)) || (rc = s.kv_self.ensure(L * b * T * 2 * d)) || (rc = s.x.ensure(b * d)) ||
       (rc = s.xn.ensure(b * d)) || (rc = s.qkv.ensure(b * 3 * d)) || (rc = s.att.ensure(b * d)) || (rc = s.hid.ensure(b * 4 * d)) ||
       (rc = s.q.ensure(b * d)) || (rc = s.tokens.ensure(b * T)) || (rc = s.lens.ensure(b)) || (rc = s.finished.ensure(b)) ||
-      (rc = s.pos.ensure(1)) || (rc = s.n_finished.ensure(1)) || (rc = s.part_val.ensure((static_cast<size_t>(w.n_vocab) / 32 + 2) * 32)) ||
-      (rc = s.part_idx.ensure((static_cast<size_t>(w.n_vocab) / 32 + 2) * 32)))
+      (rc = s.pos.ensure(1)) || (rc = s.n_finished.ensure(1)) || (rc = s.part_key.ensure(key_rows(w.n_vocab) * 32)))
     return rc;
   s.cap_B = B; s.cap_S = S; s.cap_T = T;
   uintptr_t sig = 0;
@@ -427,7 +422,7 @@ int ensure_decode_state(Replica* m, int B, int S, int T) {
                         static_cast<const void*>(s.xn.p), static_cast<const void*>(s.qkv.p), static_cast<const void*>(s.att.p),
                         static_cast<const void*>(s.hid.p), static_cast<const void*>(s.q.p), static_cast<const void*>(s.tokens.p),
                         static_cast<const void*>(s.lens.p), static_cast<const void*>(s.finished.p), static_cast<const void*>(s.pos.p),
-                        static_cast<const void*>(s.n_finished.p), static_cast<const void*>(s.part_val.p), static_cast<const void*>(s.part_idx.p)})
+                        static_cast<const void*>(s.n_finished.p), static_cast<const void*>(s.part_key.p)})
     sig = sig * 1000003u + reinterpret_cast<uintptr_t>(q);
   if (sig != s.buf_sig) {
     s.drop_graphs();
@@ -449,27 +444,27 @@ int forward_one(Replica* m, int B, int S, int T, bool want_logits, int suppress_
     const DecLayerW& lw = w.layers[l];
     // self-attention over the cache
     if ((rc = launch_layernorm(s.x.p, lw.ln1_g, lw.ln1_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
-    if ((rc = launch_dec_linear<0>(s.xn.p, B, d, lw.sa_wqkv, lw.sa_bqkv, 3 * d, s.qkv.p, 3 * d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
+    if ((rc = launch_dec_linear<0>(s.xn.p, B, d, lw.sa_wqkv, lw.sa_bqkv, 3 * d, s.qkv.p, 3 * d, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     float* cache = s.kv_self.p + static_cast<size_t>(l) * B * T * 2 * d;
     dec_self_attn_kernel<<<dim3(B, H), 128, (DH + T) * sizeof(float), st>>>(s.qkv.p, cache, T, d, s.pos.p, s.att.p);
     count_launch();
-    if ((rc = launch_dec_linear<2>(s.att.p, B, d, lw.sa_wo, lw.sa_bo, d, s.x.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
+    if ((rc = launch_dec_linear<2>(s.att.p, B, d, lw.sa_wo, lw.sa_bo, d, s.x.p, d, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     // cross-attention over the precomputed encoder K/V
     if ((rc = launch_layernorm(s.x.p, lw.ln2_g, lw.ln2_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
-    if ((rc = launch_dec_linear<0>(s.xn.p, B, d, lw.ca_wq, lw.ca_bq, d, s.q.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
+    if ((rc = launch_dec_linear<0>(s.xn.p, B, d, lw.ca_wq, lw.ca_bq, d, s.q.p, d, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     const op16* kv = s.kv_cross.p + static_cast<size_t>(l) * B * S * 2 * d;
     dec_cross_attn_kernel<<<dim3(B, H), 256, S * sizeof(float), st>>>(s.q.p, kv, S, d, s.att.p);
     count_launch();
-    if ((rc = launch_dec_linear<2>(s.att.p, B, d, lw.ca_wo, lw.ca_bo, d, s.x.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
+    if ((rc = launch_dec_linear<2>(s.att.p, B, d, lw.ca_wo, lw.ca_bo, d, s.x.p, d, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
     // FFN
     if ((rc = launch_layernorm(s.x.p, lw.ln3_g, lw.ln3_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
-    if ((rc = launch_dec_linear<1>(s.xn.p, B, d, lw.w1, lw.b1, 4 * d, s.hid.p, 4 * d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
-    if ((rc = launch_dec_linear<2>(s.hid.p, B, 4 * d, lw.w2, lw.b2, d, s.x.p, d, nullptr, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
+    if ((rc = launch_dec_linear<1>(s.xn.p, B, d, lw.w1, lw.b1, 4 * d, s.hid.p, 4 * d, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
+    if ((rc = launch_dec_linear<2>(s.hid.p, B, 4 * d, lw.w2, lw.b2, d, s.x.p, d, nullptr, nullptr, nullptr, st)) != WB_OK) return rc;
   }
   if (want_logits) {
     if ((rc = launch_layernorm(s.x.p, w.ln_g, w.ln_b, B, d, nullptr, false, s.xn.p, st)) != WB_OK) return rc;
-    if ((rc = launch_dec_linear<3>(s.xn.p, B, d, w.tok_emb, nullptr, w.n_vocab, logits_out, w.n_vocab, w.suppress[suppress_set], s.part_val.p,
-                                   s.part_idx.p, &s.argmax_blocks, st)) != WB_OK)
+    if ((rc = launch_dec_linear<3>(s.xn.p, B, d, w.tok_emb, nullptr, w.n_vocab, logits_out, w.n_vocab, w.suppress[suppress_set], s.part_key.p,
+                                   &s.argmax_groups, st)) != WB_OK)
       return rc;
   }
   WB_CUDA_OK(cudaGetLastError());
@@ -486,7 +481,7 @@ int token_step(Replica* m, int B, int S, int T, bool pick, int sup_set, float* d
     int rc = forward_one(m, B, S, T, pick, sup_set, d_logits);
     if (rc != WB_OK) return rc;
     if (pick) {
-      dec_pick_kernel<<<1, 1024, 0, st>>>(s.part_val.p, s.part_idx.p, s.argmax_blocks, B, T, s.tokens.p, s.lens.p, s.finished.p,
+      dec_pick_kernel<<<1, 1024, 0, st>>>(s.part_key.p, s.argmax_groups, B, T, s.tokens.p, s.lens.p, s.finished.p,
                                                      s.n_finished.p, s.pos.p);
       count_launch();
     }
@@ -666,7 +661,8 @@ int decoder_greedy_s(Replica* m, const op16* d_states, int B, int S, const int* 
   DevBuf<int> d_init;
   if ((rc = d_init.ensure(n_init)) != WB_OK) return rc;
   WB_CUDA_OK(cudaMemcpyAsync(d_init.p, initial_tokens, n_init * sizeof(int), cudaMemcpyHostToDevice, st));
-  dec_init_kernel<<<B, 128, 0, st>>>(s.tokens.p, T, B, d_init.p, n_init, s.lens.p, s.finished.p, s.pos.p, s.n_finished.p);
+  dec_init_kernel<<<B, 128, 0, st>>>(s.tokens.p, T, B, d_init.p, n_init, s.lens.p, s.finished.p, s.pos.p, s.n_finished.p, s.part_key.p,
+                                     static_cast<int>(key_rows(m->dec.n_vocab) * 32));
   count_launch();
   if ((rc = cross_kv(m, d_states, B, S)) != WB_OK) return rc;
   const int sup_set = suppress_timestamps ? 0 : 1;
