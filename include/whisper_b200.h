@@ -289,6 +289,9 @@ int wb_debug_attention(int device, const float* qkv, int B, int S, int d, int n_
  * launching stream, after 2 warm-up launches); *ms_per_launch receives the mean.  Kernel tuning only. */
 int wb_debug_attention_bench(int device, int B, int S, int d, int n_heads, int iters, float* ms_per_launch);
 /* Encoder::forward_mel truncated after n_layers blocks (n_layers < 0: all), with or without ln_post: stage-wise parity. */
+/* Experiment switch (default off; WB_LN_FOLLOW=1 at load): run the LayerNorm that follows a residual GEMM as a concurrent kernel
+ * fed by the GEMM's per-32-row completion counters.  Bit-identical results; measured slower under the 1 kW power cap. */
+int wb_debug_set_ln_follow(wb_model* m, int on);
 int wb_debug_encode(const wb_model* m, const float* mel, size_t mel_len, int n_layers, int ln_post, float* out,
                     size_t out_capacity);
 /* Per-kernel timing for bench.py's roofline: while enabled, every launch of the model's path is bracketed by CUDA events on

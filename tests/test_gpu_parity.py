@@ -193,6 +193,24 @@ def test_encoder_stagewise_tiny(tiny, mel0):
     assert abs(got.mean()) < 0.5 and 0.5 < got.std() < 3.0 and np.isfinite(got).all()
 
 
+@pytest.mark.parametrize("T", [3000, 1001, 70])
+def test_layernorm_follower_bit_identical(tiny, mel0, T):
+    """The experimental concurrent LayerNorm (a follower kernel fed by the residual GEMM's completion counters, off by default)
+    must give bit-identical encoder states to the separate launches: same arithmetic, different schedule -- whichever of the
+    follower and the sweep behind the GEMM normalises a row group."""
+    import whisper_apr_b200
+    model, w, cfg = tiny
+    L = whisper_apr_b200.lib()
+    ref = model.encode(mel0[:T])
+    try:
+        whisper_apr_b200._lib.check(L.wb_debug_set_ln_follow(model._h, 1))
+        for _ in range(3):                                                     # eager, captured and replayed
+            got = model.encode(mel0[:T])
+            assert np.array_equal(got, ref)
+    finally:
+        whisper_apr_b200._lib.check(L.wb_debug_set_ln_follow(model._h, 0))
+
+
 def test_encoder_matches_c_restatement(tiny, mel0):
     model, w, cfg = tiny
     ref = cref.forward_mel(mel0[:600], w, cfg, threads=4)                      # f32, reference loop structure, flash block 32

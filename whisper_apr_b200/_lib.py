@@ -72,6 +72,7 @@ SIGNATURES = {
     "wb_debug_attention": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "wb_debug_gemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "wb_debug_attention_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "wb_debug_set_ln_follow": (C.c_int, [_vp, C.c_int]),
     "wb_debug_encode": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int, _vp, C.c_size_t]),
     "wb_launch_count": (C.c_longlong, []),
     "wb_debug_apr_tensor_bytes": (C.c_longlong, [_vp, C.c_size_t, C.c_char_p]),

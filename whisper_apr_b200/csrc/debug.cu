@@ -203,6 +203,22 @@ int wb_profile_read(wb_model* h, float* ms_by_cat, int* launches_by_cat, int n_c
   return WB_OK;
 }
 
+// Experiment switch (default off, WB_LN_FOLLOW=1 turns it on at load): the LayerNorm behind a residual GEMM as a concurrent follower
+// kernel (pipeline.cu).  Captured step graphs hold the other launch sequence and are dropped.
+int wb_debug_set_ln_follow(wb_model* h, int on) {
+  if (!h) return set_error(WB_ERR_MODEL, "null model");
+  for (Replica* m : h->reps) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard guard(m->device);
+    cudaDeviceSynchronize();
+    m->ln_follow = on != 0;
+    for (auto& g : m->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
+  }
+  return WB_OK;
+}
+
 int wb_debug_encode(const wb_model* h, const float* mel, size_t mel_len, int n_layers, int ln_post, float* out, size_t out_capacity) {
   Replica* m = rep0(h);
   if (!m) return set_error(WB_ERR_MODEL, "null model");

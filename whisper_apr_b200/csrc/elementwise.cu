@@ -1,5 +1,7 @@
 // HBM-bound helpers around the tensor-core kernels: LayerNorm, dtype expansion of `.apr` payloads,
 // conv-weight repacking and guard-row fills.
+#include <algorithm>
+
 #include "ptx.cuh"
 #include "wb_internal.h"
 
@@ -10,23 +12,21 @@ namespace {
 // LayerNorm::forward (src/model/encoder.rs:219-251): per row mean, POPULATION variance (two passes, as the
 // reference), 1/sqrt(var + 1e-5), * gamma + beta.  One warp per row; the row lives in registers between the
 // passes so x is read from HBM once (4 B/elem in, 2 B/elem out for the bf16 GEMM operand).
-template <int NV>   // float4 per lane; d == 128 * nv, nv <= NV
-__global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d,
-                 uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
+// One row by one warp.  CG: read x with ld.global.cg (L2 only) -- the follower reads rows another kernel's TMA reductions have just
+// written, which must not be served from a stale L1 line.
+template <int NV, bool CG>   // float4 per lane; d == 128 * nv, nv <= NV
+__device__ __forceinline__ void ln_row(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long row,
+                                       int d, int lane, uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32) {
   const int nv = d >> 7;
   // lane l owns float4 l, l + 32, ...: every load instruction of the warp covers 512 contiguous bytes (a lane reading 32 B runs
   // instead -- tried for 16 B output stores -- touches every sector twice and cost 8 % on this HBM-bound kernel)
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
   float4 v[NV];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     if (i < nv) {
-      v[i] = xr[lane + 32 * i];
+      v[i] = CG ? __ldcg(xr + lane + 32 * i) : xr[lane + 32 * i];
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -64,9 +64,67 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
           w.x = pack_op16x2(r.x, r.y);
           w.y = pack_op16x2(r.z, r.w);
         }
-        reinterpret_cast<uint2*>(out_16 + static_cast<long long>(row) * d)[lane + 32 * i] = w;
+        reinterpret_cast<uint2*>(out_16 + row * d)[lane + 32 * i] = w;
       }
-      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * d)[lane + 32 * i] = r;
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + row * d)[lane + 32 * i] = r;
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d,
+                 uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  ln_row<NV, false>(x, gamma, beta, row, d, threadIdx.x & 31, out_16, as_bf16, out_f32);
+}
+
+// The follower: runs on its own stream BESIDE the residual GEMM that produces x (one small block per SM next to the GEMM's CTA: no
+// shared memory to speak of, no tensor memory).  Block b takes row groups b, b + gridDim, ...: the GEMM finishes them in ascending
+// order.  Thread 0 polls the group's counter (acquire) until all `need` column tiles have reduced their share into the rows, re-arms
+// it, and the block's 8 warps normalise 4 rows each straight out of L2 -- the residual stream is never re-read from HBM for its
+// LayerNorm and the LayerNorm costs no time of its own beyond the last group's few microseconds.
+// Concurrency of two kernels is never guaranteed: WAIT = true gives up after 20 ms without progress (a GEMM takes < 1 ms) and leaves
+// its remaining groups; the same kernel with WAIT = false is launched BEHIND the GEMM and normalises whatever groups still carry a
+// full counter (normally none: ~3 us).  No schedule can deadlock or skip a row.
+template <int NV, bool WAIT>
+__global__ void __launch_bounds__(256)
+layernorm_follow_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d,
+                        uint16_t* __restrict__ out_16, unsigned int* __restrict__ ready, unsigned int need) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_groups = (rows + 31) >> 5;
+  __shared__ int s_go;
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    if (threadIdx.x == 0) {
+      unsigned int c;
+      uint64_t t0 = 0;
+      unsigned int spins = 0;
+      int ok = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(ready + g) : "memory");
+        if (c >= need) { ok = 1; break; }
+        if (!WAIT) break;
+        __nanosleep(spins < 64 ? 100 : 500);
+        if ((++spins & 255u) == 0) {
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 20000000ull) break;
+        }
+      }
+      if (ok) ready[g] = 0u;                            // re-armed for the next residual GEMM (it starts after this kernel has ended)
+      s_go = ok;
+    }
+    __syncthreads();
+    const int go = s_go;
+    __syncthreads();
+    if (!go) {
+      if (WAIT) break;
+      continue;
+    }
+    for (int r = warp; r < 32; r += 8) {
+      const long long row = static_cast<long long>(g) * 32 + r;
+      if (row < rows) ln_row<NV, true>(x, gamma, beta, row, d, lane, out_16, false, nullptr);
     }
   }
 }
@@ -220,6 +278,35 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
     layernorm_generic_kernel<<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
     count_launch();
   }
+  WB_CUDA_OK(cudaGetLastError());
+  return WB_OK;
+}
+
+int launch_layernorm_follow(const float* x, const float* gamma, const float* beta, int rows, int d, op16* out, unsigned int* ready,
+                            unsigned int need, bool wait, cudaStream_t stream) {
+  if (rows <= 0) return WB_OK;
+  if (d % 128 != 0 || d > 1280) return set_error(WB_ERR_MODEL, "layernorm_follow needs d % 128 == 0 and d <= 1280");
+  // An SM has ONE L1 / shared-memory split at a time: a resident block that was launched with the default (L1-heavy) carve-out keeps
+  // a GEMM CTA that needs 213 KB of shared memory off that SM until it exits -- measured: the follower then never overlaps and times
+  // out.  Ask for the GEMM's own split (it reads x with ld.global.cg and has no use for L1 anyway).
+  static PerDeviceOnce once;
+  int rc = once.run([](int) -> int {
+    WB_CUDA_OK((cudaFuncSetAttribute(layernorm_follow_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
+    WB_CUDA_OK((cudaFuncSetAttribute(layernorm_follow_kernel<10, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
+    return WB_OK;
+  });
+  if (rc != WB_OK) return rc;
+  const int groups = (rows + 31) / 32;
+  const int grid = std::min(groups, device_sm_count());          // one block per SM, beside the GEMM's CTA
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  if (wait) {
+    if (d <= 512) layernorm_follow_kernel<4, true><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, o, ready, need);
+    else layernorm_follow_kernel<10, true><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, o, ready, need);
+  } else {
+    if (d <= 512) layernorm_follow_kernel<4, false><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, o, ready, need);
+    else layernorm_follow_kernel<10, false><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, o, ready, need);
+  }
+  count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
 }

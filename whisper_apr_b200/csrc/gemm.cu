@@ -44,6 +44,7 @@ struct GemmKParams {
   const float* bias;
   void* out;
   const float* pe;
+  unsigned int* ready;          // EPI_RESID_F32: per-32-row completion counters for a follower kernel (or nullptr)
   uint32_t idesc;               // tcgen05 instruction descriptor
 };
 
@@ -354,6 +355,16 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+      if constexpr (kResid) {
+        // tell the follower (layernorm_follow_kernel on another stream) that this column tile's share of rows row0 .. row0 + 31 is in
+        // the residual stream: the reductions are complete (wait_group, not .read), ordered before the counter by the fences
+        if (p.ready != nullptr && row0_in_batch < p.rows_per_batch && lane == 0) {
+          tma_store_wait_all();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __threadfence();
+          atomicAdd(p.ready + (row0_in_batch >> 5), 1u);
+        }
+      }
     }
     if constexpr (kResid || EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
       if (lane == 0) tma_store_wait_all();     // every store / reduction of this warp has been performed before the CTA exits
@@ -459,6 +470,11 @@ static int make_tmap_f32_3d(CUtensorMap* out, void* base, uint64_t d0, uint64_t 
   return WB_OK;
 }
 
+int gemm_tiles_n(int N) {
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  return (N + BN - 1) / BN;
+}
+
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   int rc = gemm_init();
   if (rc != WB_OK) return rc;
@@ -487,6 +503,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.bias = g.bias;
   kp.out = g.out;
   kp.pe = g.pe;
+  kp.ready = (g.epilogue == EPI_RESID_F32 && g.n_batch == 1) ? g.ready : nullptr;
   kp.idesc = umma_idesc_op16(2 * BM, BN, 0);
   const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
   CUtensorMap tc = ta;                                    // the f32 debug / positional-embedding epilogues do not read it

@@ -293,6 +293,7 @@ int load_replica(Replica* m, const AprFile& f, const uint8_t* /*pinned_base*/) {
   DeviceGuard guard(m->device);
   m->cfg = f.cfg;
   m->use_graphs = getenv("WB_NO_GRAPH") == nullptr;       // A/B switch: plain launches instead of graph replay
+  m->ln_follow = getenv("WB_LN_FOLLOW") != nullptr;       // experiment switch (default off): LayerNorm as a concurrent follower of the residual GEMMs
   if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) return set_error(WB_ERR_CUDA, "cudaStreamCreate failed");
   m->stream = m->own_stream;
   WB_CUDA_OK(cudaEventCreateWithFlags(&m->done_event, cudaEventDisableTiming));
@@ -374,6 +375,9 @@ void free_replica(Replica* m) {
     if (sl.out_done) cudaEventDestroy(sl.out_done);
   }
   if (m->done_event) cudaEventDestroy(m->done_event);
+  if (m->ln_fork) cudaEventDestroy(m->ln_fork);
+  if (m->ln_join) cudaEventDestroy(m->ln_join);
+  if (m->ln_stream) cudaStreamDestroy(m->ln_stream);
   if (m->in_stream) cudaStreamDestroy(m->in_stream);
   if (m->out_stream) cudaStreamDestroy(m->out_stream);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);

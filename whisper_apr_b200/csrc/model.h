@@ -119,6 +119,7 @@ struct Workspace {
   DevBuf<float> audio, logmel, mel_f32, x, out_f32;
   DevBuf<int> n_valid, max_key;
   DevBuf<unsigned int> mel_done;        // [B] zeroed: mel_finalize's last-block protocol
+  DevBuf<unsigned int> ln_ready;        // [rows / 32] zeroed: residual GEMM -> layernorm_follow hand-over counters (re-armed by the follower)
   DevBuf<op16> mel_bf16, c1, xn, qkv, att, hid, out_bf16;
   int guard_T = -1;                     // T for which c1's zero guard rows (conv2's padding) are in place
 };
@@ -129,6 +130,10 @@ struct Replica {
   int device = 0;
   wb_config cfg{};
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // the LayerNorm that follows a residual GEMM runs beside it on this stream (fork / join through the two events)
+  cudaStream_t ln_stream = nullptr;
+  cudaEvent_t ln_fork = nullptr, ln_join = nullptr;
+  bool ln_follow = false;               // WB_LN_FOLLOW=1 / wb_debug_set_ln_follow: experiment, measured slower under the power cap
   int max_batch = 32;
   std::mutex mu;                        // calls on one replica serialise ("concurrent calls on one handle serialise per device stream")
   std::vector<void*> allocs;            // weight allocations (freed in free_replica)

@@ -33,6 +33,8 @@ int ensure_workspace(Replica* m, int B) {
   if ((rc = w.c1.ensure(b * (T + 2) * d)) != WB_OK) return rc;
   if ((rc = w.x.ensure(b * S * d)) != WB_OK) return rc;
   if ((rc = w.xn.ensure(b * S * d)) != WB_OK) return rc;
+  if ((rc = w.ln_ready.ensure(b * S / 32 + 2)) != WB_OK) return rc;
+  WB_CUDA_OK(cudaMemsetAsync(w.ln_ready.p, 0, (b * S / 32 + 2) * sizeof(unsigned int), m->stream));
   if ((rc = w.qkv.ensure(b * S * 3 * d)) != WB_OK) return rc;
   if ((rc = w.att.ensure(b * S * d)) != WB_OK) return rc;
   if ((rc = w.hid.ensure(b * S * 4 * d)) != WB_OK) return rc;
@@ -98,19 +100,61 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   auto expand = [&](const uint8_t* packed, op16* dst, size_t n) {
     return m->quant == 2 ? launch_i8_to_op16(reinterpret_cast<const int8_t*>(packed), dst, n, st) : launch_i4_to_op16(packed, dst, n, st);
   };
+  // EXPERIMENT (off by default, WB_LN_FOLLOW=1): a residual GEMM (x += ...) and the LayerNorm of its result run SIDE BY SIDE: the
+  // LayerNorm kernel is put on a second stream before the GEMM is launched, polls the GEMM's per-32-row completion counters and
+  // normalises every row group out of L2 as soon as its last column tile has been reduced -- no HBM re-read of the residual stream, no
+  // LayerNorm time on the critical path beyond the last group.  It works (bit-identical states, 64 fewer serial launches) and it is
+  // 1-2 % SLOWER on the large-v3 step (profiles/r02w_ln_follow_ab.txt): the step is pinned at the 1 kW power cap, so hiding a low-power
+  // HBM-bound kernel under a tensor-bound one frees no energy, and the follower's polling and L2 traffic cost the GEMM a little.
+  // Off while the per-kernel profile is on and for widths the follower has no instantiation for.
+  const bool follow = m->ln_follow && !m->prof_on && d % 128 == 0 && d <= 1280 && M >= 32;
+  if (follow && !m->ln_stream) {
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&m->ln_stream, cudaStreamNonBlocking));
+    WB_CUDA_OK(cudaEventCreateWithFlags(&m->ln_fork, cudaEventDisableTiming));
+    WB_CUDA_OK(cudaEventCreateWithFlags(&m->ln_join, cudaEventDisableTiming));
+  }
+  // x += A . W^T (+ bias), then xn = LayerNorm(x; g, b) -- fused in time when `follow`
+  auto resid_then_ln = [&](const op16* A, int K, const op16* W, float alpha, const float* cs, const float* bias, const float* g, const float* bta) -> int {
+    GemmDesc q{};
+    q.A = A; q.a_row_stride = K; q.a_batch_stride = static_cast<long long>(M) * K; q.rows_per_batch = M; q.n_batch = 1;
+    q.W = W; q.N = d; q.K = K; q.epilogue = EPI_RESID_F32; q.alpha = alpha; q.col_scale = cs; q.bias = bias;
+    q.out = w.x.p; q.ldc = d; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
+    if (g == nullptr) {                                                             // no LayerNorm behind this one
+      WB_PROF(PC_GEMM, launch_gemm(q, st));
+      return WB_OK;
+    }
+    if (!follow) {
+      WB_PROF(PC_GEMM, launch_gemm(q, st));
+      WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, g, bta, M, d, w.xn.p, false, nullptr, st));
+      return WB_OK;
+    }
+    q.ready = w.ln_ready.p;
+    WB_CUDA_OK(cudaEventRecord(m->ln_fork, st));
+    WB_CUDA_OK(cudaStreamWaitEvent(m->ln_stream, m->ln_fork, 0));
+    const unsigned int need = static_cast<unsigned int>(gemm_tiles_n(d));
+    int r = launch_layernorm_follow(w.x.p, g, bta, M, d, w.xn.p, w.ln_ready.p, need, true, m->ln_stream);
+    if (r != WB_OK) return r;
+    WB_CUDA_OK(cudaEventRecord(m->ln_join, m->ln_stream));
+    r = launch_gemm(q, st);
+    WB_CUDA_OK(cudaStreamWaitEvent(st, m->ln_join, 0));
+    if (r != WB_OK) return r;
+    return launch_layernorm_follow(w.x.p, g, bta, M, d, w.xn.p, w.ln_ready.p, need, false, st);      // sweep: normally finds nothing
+  };
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = m->layers[i];
-    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, false, nullptr, st));
+    if (i == 0) { WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, false, nullptr, st)); }
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.pqkv, lw.wqkv, 3 * dd)); }
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p));
     WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.po, lw.wo, dd)); }
-    WB_PROF(PC_GEMM, flat(w.att.p, d, lw.wo, d, EPI_RESID_F32, lw.so, lw.cso, lw.bo, w.x.p));
-    WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln2_g, lw.ln2_b, M, d, w.xn.p, false, nullptr, st));
+    if ((rc = resid_then_ln(w.att.p, d, lw.wo, lw.so, lw.cso, lw.bo, lw.ln2_g, lw.ln2_b)) != WB_OK) return rc;
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p1, lw.w1, 4 * dd)); }
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.w1, 4 * d, EPI_GELU_BF16, lw.s1, lw.cs1, lw.b1, w.hid.p));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p2, lw.w2, 4 * dd)); }
-    WB_PROF(PC_GEMM, flat(w.hid.p, 4 * d, lw.w2, d, EPI_RESID_F32, lw.s2, lw.cs2, lw.b2, w.x.p));
+    // fc2's result is normalised for the NEXT layer's attention (its ln1); the last layer is followed by ln_post below
+    const bool next = i + 1 < L;
+    if ((rc = resid_then_ln(w.hid.p, 4 * d, lw.w2, lw.s2, lw.cs2, lw.b2, next ? m->layers[i + 1].ln1_g : nullptr, next ? m->layers[i + 1].ln1_b : nullptr)) != WB_OK)
+      return rc;
   }
   if (ln_post) {
     // 16-bit states: bf16 when the caller asked for WB_BF16 (a user-facing format), the operand format when they feed the decoder's

@@ -106,7 +106,12 @@ struct GemmDesc {
   int out_rows_per_batch;
   int out_row_off;
   const float* pe;            // EPI_GELU_PE_F32: [>=rows_per_batch][N] f32
+  // EPI_RESID_F32 with n_batch == 1, optional: ready[r / 32] is incremented once per column tile when that tile's reductions into rows
+  // [32 (r / 32), +32) have been performed -- a kernel running BESIDE the GEMM (layernorm_follow) picks a row group up as soon as its
+  // counter reaches gemm_tiles_n(N) and finds the rows in L2.  nullptr: no signalling.
+  unsigned int* ready = nullptr;
 };
+int gemm_tiles_n(int N);      // column tiles launch_gemm cuts N into
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
 int gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
@@ -168,6 +173,12 @@ int mel_init();
 // ---- elementwise / normalisation
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, void* out_16, bool out_16_is_bf16,
                      float* out_f32, cudaStream_t stream);
+// LayerNorm that FOLLOWS a residual GEMM running on another stream: row group g (32 rows) is normalised as soon as ready[g] == need
+// (GemmDesc::ready), read through L2, and the counter is re-armed to 0.  Same arithmetic as launch_layernorm (op16 output only).
+// wait = true: the concurrent form (gives up after 20 ms without progress); wait = false: the sweep behind the GEMM that normalises
+// every group still carrying a full counter.  Launch both: together they cover every row under any kernel schedule.
+int launch_layernorm_follow(const float* x, const float* gamma, const float* beta, int rows, int d, op16* out, unsigned int* ready,
+                            unsigned int need, bool wait, cudaStream_t stream);
 int launch_f32_to_op16(const float* in, op16* out, size_t n, cudaStream_t stream);
 int launch_i8_to_op16(const int8_t* in, op16* out, size_t n, cudaStream_t stream);
 int launch_i4_to_op16(const uint8_t* in, op16* out, size_t n, cudaStream_t stream);
