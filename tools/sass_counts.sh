@@ -17,3 +17,6 @@ cuobjdump -sass build/obj/gemm.cu.o | grep -oE "UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-
 echo
 echo "# variants inside attention.cu.o (STTM = tcgen05.st of P into tensor memory; UTCHMMA with a TMEM A operand)"
 cuobjdump -sass build/obj/attention.cu.o | grep -oE "UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9]*|LDTM[.a-zA-Z0-9]*|STTM[.a-zA-Z0-9]*|UTCBAR[.A-Z0-9]*" | sort | uniq -c
+echo
+echo "# packed fp32x2 arithmetic in mel.cu.o (one instruction per complex operation; scalar counterparts beside them)"
+cuobjdump -sass build/obj/mel.cu.o | grep -oE "\b(FADD2|FMUL2|FFMA2|FADD|FMUL|FFMA)\b" | sort | uniq -c
