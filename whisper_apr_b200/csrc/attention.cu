@@ -39,6 +39,7 @@ constexpr int BQ = 128, BKV = 128, DH = 64;
 constexpr int Q_TILE_BYTES = BQ * DH * 2;          // 16 KB
 constexpr int KV_TILE_BYTES = BKV * DH * 2;        // 16 KB
 constexpr int KV_STAGES = 4;
+constexpr int TAIL_KEYS = 96;                       // a last KV block with <= 96 keys runs as a 96-key block (1500 = 11 * 128 + 92)
 constexpr int TM_THREADS = 384;
 constexpr int TM_SMEM = 4 * Q_TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 256;
 constexpr uint32_t TM_COLS = 512, COL_S = 0, COL_O = 256, COL_P = 384;
@@ -50,6 +51,7 @@ struct AttnTmParams {
   float scale_log2;
   op16* out;
   int use_token;
+  int tail_keys;                      // a last KV block with at most this many keys runs as a 96-key block (0: never)
   uint32_t rt_zero;                   // 0, but only known at run time (exp_row's ordering trick)
 };
 
@@ -99,12 +101,16 @@ __device__ __forceinline__ float exp2_fma_pipe(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int POLY>   // 0: every exponential on the MUFU; n > 0: one pair in n goes to the FMA pipe instead; n < 0: MUFU only, consumers lag
+// POLY 0: every exponential on the MUFU; n > 0: one pair in n goes to the FMA pipe instead; n < 0: MUFU only, consumers lag.
+// NP: pairs of the row that exist (64 = a full 128-key block; 48 = the short tail block, whose last 32 columns are never computed).
+template <int POLY, int NP>
 __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb, uint32_t rt_zero) {
   float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = NP; i < 64; ++i) pk[i] = 0u;               // stored with the rest, never read by the shortened PV product
   if (POLY >= 0) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) {
+    for (int i = 0; i < NP; ++i) {
       const float x0 = fmaf(__uint_as_float(s[2 * i]), c, -mb), x1 = fmaf(__uint_as_float(s[2 * i + 1]), c, -mb);
       float e0, e1;
       constexpr int PERIOD = POLY > 0 ? POLY : 1;
@@ -124,8 +130,8 @@ __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk
     constexpr int LAG = -POLY;
     float e[128];
 #pragma unroll
-    for (int i = 0; i < 64 + LAG; ++i) {
-      if (i < 64) {
+    for (int i = 0; i < NP + LAG; ++i) {
+      if (i < NP) {
         e[2 * i] = fast_exp2(fmaf(__uint_as_float(s[2 * i]), c, -mb));
         e[2 * i + 1] = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), c, -mb));
       }
@@ -134,7 +140,7 @@ __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk
         float b = e[2 * j + 1];
         // b | (bits(e of pair i) & 0): one LOP3 whose third operand is a RUN-TIME zero, so neither nvcc nor ptxas can drop the
         // dependence -- the sum of pair j is ordered after the exponentials of pair i = j + LAG
-        if (i < 64) b = __uint_as_float(__float_as_uint(b) | (__float_as_uint(e[2 * i + 1]) & rt_zero));
+        if (i < NP) b = __uint_as_float(__float_as_uint(b) | (__float_as_uint(e[2 * i + 1]) & rt_zero));
         rs4[j & 3] += e[2 * j] + b;
         pk[j] = pack_op16x2(e[2 * j], e[2 * j + 1]);
       }
@@ -212,6 +218,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
       if (lane == 0) {
         // ------------------------------------------------------------------ S_t = Q_t K^T issuer (both tiles)
         constexpr uint32_t idesc_s = umma_idesc_op16(BQ, BKV, 0);
+        constexpr uint32_t idesc_s_tail = umma_idesc_op16(BQ, TAIL_KEYS, 0);     // short tail block: 96 key columns instead of 128
+        const bool short_tail = p.S - (n - 1) * BKV <= p.tail_keys;
         uint32_t g = 0;
         int it = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
@@ -227,8 +235,9 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
             for (int t = 0; t < 2; ++t) {
               if (g >= 1) mbar_wait(&s_free[t], (g - 1) & 1u);         // the softmax warpgroup holds S_t(g-1) in registers
               tc_fence_after_sync();
+              const uint32_t idesc = (short_tail && j == n - 1) ? idesc_s_tail : idesc_s;
 #pragma unroll
-              for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + COL_S + t * 128, qd[t] + 2 * k, kd + 2 * k, idesc_s, k != 0);
+              for (int k = 0; k < DH / 16; ++k) umma_f16(tmem_base + COL_S + t * 128, qd[t] + 2 * k, kd + 2 * k, idesc, k != 0);
               umma_commit(&s_full[t]);
             }
             umma_commit(&kv_empty[st]);
@@ -243,6 +252,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
         const int t = warp - 2;
         const uint32_t tO = tmem_base + COL_O + t * 64;
         const uint32_t tP = tmem_base + COL_P + t * 64;
+        const bool short_tail = p.S - (n - 1) * BKV <= p.tail_keys;
         uint32_t g = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           for (int j = 0; j < n; ++j, ++g) {
@@ -251,8 +261,10 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
             mbar_wait(&p_full[t], g & 1u);                              // P_t(g) is in TMEM
             tc_fence_after_sync();
             const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * KV_TILE_BYTES));
+            const int ksteps = (short_tail && j == n - 1) ? TAIL_KEYS / 16 : BKV / 16;    // keys past the tail's 96 are never multiplied
 #pragma unroll
-            for (int k = 0; k < BKV / 16; ++k) umma_f16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_o, (j | k) != 0);
+            for (int k = 0; k < BKV / 16; ++k)
+              if (k < ksteps) umma_f16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_o, (j | k) != 0);
             umma_commit(&pv_done[t]);
             umma_commit(&kv_empty[st]);
           }
@@ -278,27 +290,31 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
       int q0, h, b;
       item_coords(p, item, q0, h, b);
       float m_ref = -INFINITY, l_run = 0.f;
-      // one KV block; `masked` selects the tail-block variant (keeps the compare/select instructions out of the common path)
-      auto block_body = [&](int j, auto masked) {
+      // one KV block; `kind` selects the variant: 0 = a full block (no compare/select instructions in the common path), 128 = a
+      // masked tail block, 96 = a masked tail block with at most 96 keys: its last 32 score columns are neither computed by the
+      // QK^T product, nor loaded, nor exponentiated, nor multiplied into O (S = 1500: 92 keys, a quarter of the tail block's work)
+      auto block_body = [&](int j, auto kind) {
+        constexpr int KIND = decltype(kind)::value;
+        constexpr int NCOL = KIND == 0 ? BKV : KIND;
         mbar_wait(&s_full[t], g & 1u);
         tc_fence_after_sync();
         uint32_t s[128];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(tS + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q * 32]));
+        for (int q = 0; q < NCOL / 32; ++q) tmem_ld_32x32b_x32(tS + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q * 32]));
         bool pv_ok = g == 0;                                 // P_t / O_t are free once PV of the previous block retired (waited late)
         tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);              // S_t(g+1) may now overwrite S_t
-        if constexpr (decltype(masked)::value) {
+        if constexpr (KIND != 0) {
           const int kv_valid = p.S - j * BKV;
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
+          for (int i = 0; i < NCOL; ++i)
             if (i >= kv_valid) s[i] = 0xff800000u;           // -inf
         }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])));
+        for (int i = 0; i < NCOL / 2; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])));
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
         const bool need = (mx - m_ref) * c > 8.0f;
@@ -325,7 +341,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
         // ping-pong token: MUFU phases of the two warpgroups alternate
         if (p.use_token) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
         uint32_t pk[64];
-        const float rsum = exp_row<POLY>(s, pk, c, mb, p.rt_zero);
+        const float rsum = exp_row<POLY, NCOL / 2>(s, pk, c, mb, p.rt_zero);
         if (p.use_token && !(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
         l_run = l_run * alpha + rsum;
         if (!pv_ok) mbar_wait(&pv_done[t], (g - 1) & 1u);    // PV of the previous block has read P_t
@@ -338,8 +354,10 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
         if (lane == 0) mbar_arrive(&p_full[t]);
       };
       for (int j = 0; j < n; ++j, ++g) {
-        if (p.S - j * BKV < BKV) block_body(j, std::true_type{});
-        else block_body(j, std::false_type{});
+        const int kv_left = p.S - j * BKV;
+        if (kv_left >= BKV) block_body(j, std::integral_constant<int, 0>{});
+        else if (kv_left <= p.tail_keys) block_body(j, std::integral_constant<int, TAIL_KEYS>{});
+        else block_body(j, std::integral_constant<int, BKV>{});
       }
       // epilogue: O_t / l  (attention.rs:334-343: 0 when the sum is <= 1e-10)
       mbar_wait(&pv_done[t], (g - 1) & 1u);
@@ -407,6 +425,8 @@ int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_head
   p.out = out;
   static const int no_token = getenv("WB_ATTN_NOTOKEN") != nullptr;       // tuning switch
   p.use_token = no_token ? 0 : 1;
+  static const int no_short_tail = getenv("WB_ATTN_NO_SHORT_TAIL") != nullptr;   // A/B switch
+  p.tail_keys = no_short_tail ? 0 : TAIL_KEYS;
   p.rt_zero = 0;
   const int sms = device_sm_count();
   const int grid = p.n_items < sms ? p.n_items : sms;
