@@ -70,13 +70,11 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // for an L2 round trip eight times per tile), and the residual row prefetched one chunk ahead.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&v)[32], long long out_row, int r_in_batch, int n0,
-                                               const float* s_scale, const float* s_bias) {
+                                               uint32_t s_scale, uint32_t s_bias) {
   float acc[32];
-  const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
-  const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 sc = sc4[i], bi = bi4[i];
+    const float4 sc = lds_f4(s_scale + 16 * i), bi = lds_f4(s_bias + 16 * i);
     acc[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), sc.x, bi.x);
     acc[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, bi.y);
     acc[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, bi.z);
@@ -124,10 +122,14 @@ template <int BN>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's half of the W tile
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = (BN == 256) ? 5 : 7;      // one stage less than fits: the room went to the second staging tile below
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = 2 * 2 * BN * 4;        // per-tile scale and bias vectors, double buffered
-  static constexpr int STAGE_C_BYTES = 4 * 32 * 32 * 4;   // one 32 x 32 f32 staging tile per epilogue warp (TMA reduce-add source)
+  // TWO 4 KB staging tiles per epilogue warp (32 x 32 f32 for the TMA reduce-add, 32 x 64 op16 for the TMA store): the warp fills one
+  // while the TMA engine still reads the other.  With one tile every chunk waited out the previous store's read of shared memory
+  // (~1 us each, 4-8 times per tile): ~5 us of epilogue per tile against 2.2 us of MMAs at K = 512, and as long as the whole K = 1280
+  // mainloop -- the reason the 16-bit-output GEMMs ran the tensor pipe at 85 % where the residual ones reached 97 %.
+  static constexpr int STAGE_C_BYTES = 2 * 4 * 32 * 32 * 4;
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + STAGE_C_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -238,6 +240,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int NCH = BN / 32;
     constexpr bool kResid = EPI == EPI_RESID_F32;
     uint32_t it = 0;
+    uint32_t sbuf = 0;                                          // staging tile in use (alternates per store, across tiles)
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
       const uint32_t buf = it & 1u;
       const uint32_t use = it >> 1;
@@ -249,13 +252,15 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool row_ok = r_in_batch < p.rows_per_batch;
       const long long out_row = static_cast<long long>(b) * p.out_rows_per_batch + p.out_row_off + r_in_batch;
       // stage this tile's per-column scale (alpha x dequantisation scale) and bias; columns past N get 0
-      float* sc = s_scale + buf * BN;
-      float* bi = s_bias + buf * BN;
-      for (int i = et; i < BN; i += 128) {
+      const uint32_t sc = smem_u32(s_scale + buf * BN);      // shared-window addresses: LDS / STS, not generic loads (see lds_f4)
+      const uint32_t bi = smem_u32(s_bias + buf * BN);
+#pragma unroll
+      for (int i0 = 0; i0 < BN; i0 += 128) {
+        const int i = i0 + et;
         const int nn = nb * BN + i;
         const bool ok = nn < p.N;
-        sc[i] = ok ? p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + nn) : 1.0f) : 0.f;
-        bi[i] = (ok && p.bias != nullptr) ? __ldg(p.bias + nn) : 0.f;
+        sts_f1(sc + 4 * i, ok ? p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + nn) : 1.0f) : 0.f);
+        sts_f1(bi + 4 * i, (ok && p.bias != nullptr) ? __ldg(p.bias + nn) : 0.f);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");          // scale / bias visible to the four epilogue warps
       mbar_wait(&tfull[buf], use & 1u);
@@ -265,21 +270,27 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // the residual stream by a TMA reduction -- the L2 does the read-modify-write, rows past the end of the batch entry are
       // clipped by the tensor map.  (Row-per-lane global loads/stores cost 32 L1 wavefronts per instruction: 16k cycles per
       // tile, more than the whole K = 1280 mainloop.)
-      uint8_t* stage = sC + q * (32 * 32 * 4);
-      const uint32_t stage_row = smem_u32(stage) + lane * 128;
+      uint8_t* const stage_base = sC + q * (2 * 32 * 32 * 4);          // this warp's two staging tiles; `sbuf` alternates between them
+      uint8_t* stage = stage_base + sbuf * (32 * 32 * 4);
+      uint32_t stage_row = smem_u32(stage) + lane * 128;
+      auto next_stage = [&]() {
+        sbuf ^= 1u;
+        stage = stage_base + sbuf * (32 * 32 * 4);
+        stage_row = smem_u32(stage) + lane * 128;
+      };
       const int row0_in_batch = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32;
       auto process = [&](const uint32_t (&v)[32], int c) {
         const int n0 = nb * BN + c * 32;
         if (n0 >= p.N) return;
         if constexpr (kResid) {
           if (row0_in_batch >= p.rows_per_batch) return;      // warp-uniform: nothing of this warp's rows exists
-          const float4* sc4 = reinterpret_cast<const float4*>(sc + c * 32);
-          const float4* bi4 = reinterpret_cast<const float4*>(bi + c * 32);
-          if (lane == 0) tma_store_wait_read<0>();            // the previous chunk's reduction has read the staging tile
+          const uint32_t sc4 = sc + c * 128, bi4 = bi + c * 128;
+          next_stage();
+          if (lane == 0) tma_store_wait_read<1>();            // the reduction issued two chunks ago has read this staging tile
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 s4 = sc4[i], b4 = bi4[i];
+            const float4 s4 = lds_f4(sc4 + 16 * i), b4 = lds_f4(bi4 + 16 * i);
             const float x0 = fmaf(__uint_as_float(v[4 * i + 0]), s4.x, b4.x), x1 = fmaf(__uint_as_float(v[4 * i + 1]), s4.y, b4.y);
             const float x2 = fmaf(__uint_as_float(v[4 * i + 2]), s4.z, b4.z), x3 = fmaf(__uint_as_float(v[4 * i + 3]), s4.w, b4.w);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((static_cast<uint32_t>(i) ^ (lane & 7u)) << 4)), "f"(x0),
@@ -293,7 +304,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_store_commit();
           }
         } else {
-          if (row_ok) epilogue_chunk<EPI>(p, v, out_row, r_in_batch, n0, sc + c * 32, bi + c * 32);
+          if (row_ok) epilogue_chunk<EPI>(p, v, out_row, r_in_batch, n0, sc + c * 128, bi + c * 128);
         }
       };
       // bf16 outputs: two 32-column chunks make one 32 x 64 bf16 (128 B per row) staging tile, written with conflict-free 16 B
@@ -301,11 +312,10 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // L1 / shared-memory data pipe is already ~full with the TMA operand writes and the tensor core's operand reads.
       constexpr bool kBf16Out = EPI == EPI_BF16 || EPI == EPI_GELU_BF16;
       auto half_bf16 = [&](const uint32_t (&v)[32], int c, int half) {
-        const float4* sc4 = reinterpret_cast<const float4*>(sc + c * 32);
-        const float4* bi4 = reinterpret_cast<const float4*>(bi + c * 32);
+        const uint32_t sc4 = sc + c * 128, bi4 = bi + c * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                         // 8 columns -> one 16 B store
-          const float4 s0 = sc4[2 * i], b0 = bi4[2 * i], s1 = sc4[2 * i + 1], b1 = bi4[2 * i + 1];
+          const float4 s0 = lds_f4(sc4 + 32 * i), b0 = lds_f4(bi4 + 32 * i), s1 = lds_f4(sc4 + 32 * i + 16), b1 = lds_f4(bi4 + 32 * i + 16);
           float a[8];
           a[0] = fmaf(__uint_as_float(v[8 * i + 0]), s0.x, b0.x); a[1] = fmaf(__uint_as_float(v[8 * i + 1]), s0.y, b0.y);
           a[2] = fmaf(__uint_as_float(v[8 * i + 2]), s0.z, b0.z); a[3] = fmaf(__uint_as_float(v[8 * i + 3]), s0.w, b0.w);
@@ -330,7 +340,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (kBf16Out) {
           const bool live = nb * BN + c * 32 < p.N && row0_in_batch < p.rows_per_batch;       // warp-uniform
           if (live) {
-            if (lane == 0) tma_store_wait_read<0>();          // the previous pair's store has read the staging tile
+            next_stage();
+            if (lane == 0) tma_store_wait_read<1>();          // the store issued two pairs ago has read this staging tile
             __syncwarp();
             half_bf16(v0, c, 0);
           }
