@@ -6,10 +6,11 @@
 // W stored [out][in]) and Conv1d::forward (src/model/encoder.rs:72-110) of the reference.  Both operands are
 // K-major bf16, accumulation is fp32 in tensor memory.
 //
-// Kernel shape: persistent, a cluster of two CTAs (the two SMs of a TPC, tcgen05 cta_group::2) per 256 x BN tile, 192 threads per CTA:
+// Kernel shape: persistent, a cluster of two CTAs (the two SMs of a TPC, tcgen05 cta_group::2) per 256 x BN tile, 320 threads per CTA:
 //   warp 0      TMA producer: this CTA's 128 rows of A and its half of the W tile per 64-wide k-block, 128-byte swizzle
 //   warp 1      TMEM allocator; in the leader CTA the single-thread issuer of tcgen05.mma.cta_group::2 (256 x BN x 16)
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns (double buffered), per-column scale + bias from shared memory,
+//   warps 2..9  epilogue, two warps per TMEM lane quarter, each half of the tile's columns: tcgen05.ld 32 lanes x 32 columns (double
+//               buffered), per-column scale + bias from shared memory,
 //               GELU; bf16 results and the fp32 residual update leave through shared-memory staging tiles and TMA
 //               (cp.async.bulk.tensor store / cp.reduce.async.bulk.tensor .add) -- no row-per-lane global accesses
 // Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA, multicast commits), two TMEM accumulator buffers (MMA <-> epilogue),
@@ -32,7 +33,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmKParams {
   int rows_per_batch, n_batch, N, K;
@@ -122,14 +123,15 @@ template <int BN>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's half of the W tile
-  static constexpr int STAGES = (BN == 256) ? 5 : 7;      // one stage less than fits: the room went to the second staging tile below
+  static constexpr int STAGES = (BN == 256) ? 5 : 7;      // one stage less than fits: the room went to the eight epilogue warps' staging tiles
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = 2 * 2 * BN * 4;        // per-tile scale and bias vectors, double buffered
-  // TWO 4 KB staging tiles per epilogue warp (32 x 32 f32 for the TMA reduce-add, 32 x 64 op16 for the TMA store): the warp fills one
-  // while the TMA engine still reads the other.  With one tile every chunk waited out the previous store's read of shared memory
-  // (~1 us each, 4-8 times per tile): ~5 us of epilogue per tile against 2.2 us of MMAs at K = 512, and as long as the whole K = 1280
-  // mainloop -- the reason the 16-bit-output GEMMs ran the tensor pipe at 85 % where the residual ones reached 97 %.
-  static constexpr int STAGE_C_BYTES = 2 * 4 * 32 * 32 * 4;
+  // One 4 KB staging tile per epilogue warp (32 x 32 f32 for the TMA reduce-add, 32 x 64 op16 for the TMA store), EIGHT epilogue
+  // warps: two per TMEM lane quarter (= per scheduler), each taking half of the tile's columns.  With four warps -- one per scheduler,
+  // in-order, every chunk waiting out the previous store's read of its staging tile and the latency of its own GELU chain -- a tile's
+  // epilogue took ~5 us against 2.2 us of MMAs at K = 512 and about as long as the whole K = 1280 mainloop: the reason the
+  // 16-bit-output GEMMs ran the tensor pipe at 85 % where the residual ones reached 97 % (profiles/r02z_*).
+  static constexpr int STAGE_C_BYTES = 8 * 32 * 32 * 4;
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + STAGE_C_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -160,7 +162,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }      // 8 epilogue warps x 2 CTAs
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -232,15 +234,15 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue (warps 2..5 of both CTAs)
-    const int q = warp & 3;
-    const int et = static_cast<int>(threadIdx.x) - 64;      // 0..127 among the epilogue threads
+    // -------------------------------------------------------------- epilogue (warps 2..9 of both CTAs)
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 2) >> 2;                       // which half of the tile's column chunks this warp takes
+    const int et = static_cast<int>(threadIdx.x) - 64;      // 0..255 among the epilogue threads
     float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);    // [2][BN]
     float* s_bias = s_scale + 2 * BN;                                                                 // [2][BN]
     constexpr int NCH = BN / 32;
     constexpr bool kResid = EPI == EPI_RESID_F32;
     uint32_t it = 0;
-    uint32_t sbuf = 0;                                          // staging tile in use (alternates per store, across tiles)
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
       const uint32_t buf = it & 1u;
       const uint32_t use = it >> 1;
@@ -255,14 +257,15 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t sc = smem_u32(s_scale + buf * BN);      // shared-window addresses: LDS / STS, not generic loads (see lds_f4)
       const uint32_t bi = smem_u32(s_bias + buf * BN);
 #pragma unroll
-      for (int i0 = 0; i0 < BN; i0 += 128) {
+      for (int i0 = 0; i0 < BN; i0 += 256) {
         const int i = i0 + et;
+        if (BN < 256 && i >= BN) break;
         const int nn = nb * BN + i;
         const bool ok = nn < p.N;
         sts_f1(sc + 4 * i, ok ? p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + nn) : 1.0f) : 0.f);
         sts_f1(bi + 4 * i, (ok && p.bias != nullptr) ? __ldg(p.bias + nn) : 0.f);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // scale / bias visible to the four epilogue warps
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // scale / bias visible to the eight epilogue warps
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -270,14 +273,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // the residual stream by a TMA reduction -- the L2 does the read-modify-write, rows past the end of the batch entry are
       // clipped by the tensor map.  (Row-per-lane global loads/stores cost 32 L1 wavefronts per instruction: 16k cycles per
       // tile, more than the whole K = 1280 mainloop.)
-      uint8_t* const stage_base = sC + q * (2 * 32 * 32 * 4);          // this warp's two staging tiles; `sbuf` alternates between them
-      uint8_t* stage = stage_base + sbuf * (32 * 32 * 4);
-      uint32_t stage_row = smem_u32(stage) + lane * 128;
-      auto next_stage = [&]() {
-        sbuf ^= 1u;
-        stage = stage_base + sbuf * (32 * 32 * 4);
-        stage_row = smem_u32(stage) + lane * 128;
-      };
+      uint8_t* const stage = sC + (warp - 2) * (32 * 32 * 4);          // this warp's staging tile
+      const uint32_t stage_row = smem_u32(stage) + lane * 128;
       const int row0_in_batch = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32;
       auto process = [&](const uint32_t (&v)[32], int c) {
         const int n0 = nb * BN + c * 32;
@@ -285,8 +282,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (kResid) {
           if (row0_in_batch >= p.rows_per_batch) return;      // warp-uniform: nothing of this warp's rows exists
           const uint32_t sc4 = sc + c * 128, bi4 = bi + c * 128;
-          next_stage();
-          if (lane == 0) tma_store_wait_read<1>();            // the reduction issued two chunks ago has read this staging tile
+          if (lane == 0) tma_store_wait_read<0>();            // the previous chunk's reduction has read the staging tile
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -311,7 +307,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // shared-memory stores and sent out by one TMA store.  Row-per-lane STG.128 costs 32 L1 wavefronts per instruction, and the
       // L1 / shared-memory data pipe is already ~full with the TMA operand writes and the tensor core's operand reads.
       constexpr bool kBf16Out = EPI == EPI_BF16 || EPI == EPI_GELU_BF16;
-      auto half_bf16 = [&](const uint32_t (&v)[32], int c, int half) {
+      auto half_bf16 = [&](const uint32_t (&v)[32], int c, int hh) {
         const uint32_t sc4 = sc + c * 128, bi4 = bi + c * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                         // 8 columns -> one 16 B store
@@ -325,28 +321,29 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 8; ++k) a[k] = gelu_tanh_approx(a[k]);
           }
-          const uint32_t j = static_cast<uint32_t>(half * 4 + i);
+          const uint32_t j = static_cast<uint32_t>(hh * 4 + i);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pack_op16x2(a[0], a[1])),
                        "r"(pack_op16x2(a[2], a[3])), "r"(pack_op16x2(a[4], a[5])), "r"(pack_op16x2(a[6], a[7]))
                        : "memory");
         }
       };
       uint32_t v0[32], v1[32];
-      tmem_ld_32x32b_x32(t_row, v0);
+      constexpr int NCW = NCH / 2;                              // chunks per warp
+      const int c_lo = half * NCW, c_hi = c_lo + NCW;
+      tmem_ld_32x32b_x32(t_row + c_lo * 32, v0);
 #pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
+      for (int c = c_lo; c < c_hi; c += 2) {
         tmem_ld_wait();
         tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v1);
         if constexpr (kBf16Out) {
           const bool live = nb * BN + c * 32 < p.N && row0_in_batch < p.rows_per_batch;       // warp-uniform
           if (live) {
-            next_stage();
-            if (lane == 0) tma_store_wait_read<1>();          // the store issued two pairs ago has read this staging tile
+            if (lane == 0) tma_store_wait_read<0>();          // the previous pair's store has read the staging tile
             __syncwarp();
             half_bf16(v0, c, 0);
           }
           tmem_ld_wait();
-          if (c + 2 < NCH) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
+          if (c + 2 < c_hi) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
           if (live) {
             half_bf16(v1, c + 1, 1);                          // columns past N (N % 64 == 32) are clipped by the tensor map
             fence_proxy_async_smem();
@@ -359,7 +356,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
           process(v0, c);
           tmem_ld_wait();
-          if (c + 2 < NCH) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
+          if (c + 2 < c_hi) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, v0);
           process(v1, c + 1);
         }
       }
@@ -481,9 +478,9 @@ static int make_tmap_f32_3d(CUtensorMap* out, void* base, uint64_t d0, uint64_t 
   return WB_OK;
 }
 
-int gemm_tiles_n(int N) {
+int gemm_tiles_n(int N) {                                   // arrivals per 32-row group on GemmDesc::ready: two epilogue warps per column tile
   const int BN = (N % 256 == 0) ? 256 : 128;
-  return (N + BN - 1) / BN;
+  return 2 * ((N + BN - 1) / BN);
 }
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
