@@ -6,10 +6,11 @@
 // W stored [out][in]) and Conv1d::forward (src/model/encoder.rs:72-110) of the reference.  Both operands are
 // K-major bf16, accumulation is fp32 in tensor memory.
 //
-// Kernel shape: persistent, a cluster of two CTAs (the two SMs of a TPC, tcgen05 cta_group::2) per 256 x BN tile, 320 threads per CTA:
+// Kernel shape: persistent, a cluster of two CTAs (the two SMs of a TPC, tcgen05 cta_group::2) per 256 x BN tile, 192 or 320 threads per CTA:
 //   warp 0      TMA producer: this CTA's 128 rows of A and its half of the W tile per 64-wide k-block, 128-byte swizzle
 //   warp 1      TMEM allocator; in the leader CTA the single-thread issuer of tcgen05.mma.cta_group::2 (256 x BN x 16)
-//   warps 2..9  epilogue, two warps per TMEM lane quarter, each half of the tile's columns: tcgen05.ld 32 lanes x 32 columns (double
+//   warps 2..   epilogue: 8 warps (two per TMEM lane quarter, half of the tile's columns each) for 16-bit / GELU outputs, 4 for the
+//               residual reduce-add (Gemm2Cfg): tcgen05.ld 32 lanes x 32 columns (double
 //               buffered), per-column scale + bias from shared memory,
 //               GELU; bf16 results and the fp32 residual update leave through shared-memory staging tiles and TMA
 //               (cp.async.bulk.tensor store / cp.reduce.async.bulk.tensor .add) -- no row-per-lane global accesses
@@ -33,7 +34,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps
+constexpr int GEMM_MAX_THREADS = 320;     // TMA warp, MMA warp, up to 8 epilogue warps
 
 struct GemmKParams {
   int rows_per_batch, n_batch, N, K;
@@ -119,11 +120,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
 // both halves, and each CTA's TMEM receives its own 128 accumulator rows.  Per SM this halves the W traffic through shared
 // memory and L2 (the 1-CTA kernel needs 96 B/clk of operand reads plus 96 B/clk of TMA writes against a 128 B/clk shared-memory
 // port), which is what bounds the 1-CTA kernel at ~75 % of the cuBLAS rate.
-template <int BN>
+template <int BN, int EPI>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's half of the W tile
-  static constexpr int STAGES = (BN == 256) ? 5 : 7;      // one stage less than fits: the room went to the eight epilogue warps' staging tiles
+  // Epilogue warps: 8 (two per TMEM lane quarter) where the epilogue computes and converts (16-bit outputs, GELU), 4 for the residual
+  // reduce-add, whose epilogue is a scale + bias and whose mainloops are the long ones: there the sixth pipeline stage is worth more
+  // than the extra warps (8 warps + 5 stages: out_proj 120 -> 136 us, fc2 429 -> 426 us under ncu; 4 warps + 6 stages kept).
+  static constexpr int EPI_WARPS = (EPI == EPI_RESID_F32) ? 4 : 8;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int STAGES = (BN == 256 ? 5 : 7) + (EPI_WARPS == 4 ? 1 : 0);
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = 2 * 2 * BN * 4;        // per-tile scale and bias vectors, double buffered
   // One 4 KB staging tile per epilogue warp (32 x 32 f32 for the TMA reduce-add, 32 x 64 op16 for the TMA store), EIGHT epilogue
@@ -131,17 +137,18 @@ struct Gemm2Cfg {
   // in-order, every chunk waiting out the previous store's read of its staging tile and the latency of its own GELU chain -- a tile's
   // epilogue took ~5 us against 2.2 us of MMAs at K = 512 and about as long as the whole K = 1280 mainloop: the reason the
   // 16-bit-output GEMMs ran the tensor pipe at 85 % where the residual ones reached 97 % (profiles/r02z_*).
-  static constexpr int STAGE_C_BYTES = 8 * 32 * 32 * 4;
+  static constexpr int STAGE_C_BYTES = EPI_WARPS * 32 * 32 * 4;
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + STAGE_C_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
 template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                 const GemmKParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int EW = Cfg::EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
@@ -162,7 +169,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }      // 8 epilogue warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * EW); }      // every epilogue warp of both CTAs
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -236,8 +243,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..9 of both CTAs)
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read (warp id % 4)
-    const int half = (warp - 2) >> 2;                       // which half of the tile's column chunks this warp takes
-    const int et = static_cast<int>(threadIdx.x) - 64;      // 0..255 among the epilogue threads
+    const int half = (warp - 2) >> 2;                       // which share of the tile's column chunks this warp takes (EW / 4 shares)
+    const int et = static_cast<int>(threadIdx.x) - 64;      // 0 .. 32 EW - 1 among the epilogue threads
     float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);    // [2][BN]
     float* s_bias = s_scale + 2 * BN;                                                                 // [2][BN]
     constexpr int NCH = BN / 32;
@@ -257,15 +264,15 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t sc = smem_u32(s_scale + buf * BN);      // shared-window addresses: LDS / STS, not generic loads (see lds_f4)
       const uint32_t bi = smem_u32(s_bias + buf * BN);
 #pragma unroll
-      for (int i0 = 0; i0 < BN; i0 += 256) {
+      for (int i0 = 0; i0 < BN; i0 += 32 * EW) {
         const int i = i0 + et;
-        if (BN < 256 && i >= BN) break;
+        if (BN < 32 * EW && i >= BN) break;
         const int nn = nb * BN + i;
         const bool ok = nn < p.N;
         sts_f1(sc + 4 * i, ok ? p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + nn) : 1.0f) : 0.f);
         sts_f1(bi + 4 * i, (ok && p.bias != nullptr) ? __ldg(p.bias + nn) : 0.f);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");          // scale / bias visible to the eight epilogue warps
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");          // scale / bias visible to every epilogue warp
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -328,7 +335,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       };
       uint32_t v0[32], v1[32];
-      constexpr int NCW = NCH / 2;                              // chunks per warp
+      constexpr int NCW = NCH / (EW / 4);                       // chunks per warp
       const int c_lo = half * NCW, c_hi = c_lo + NCW;
       tmem_ld_32x32b_x32(t_row + c_lo * 32, v0);
 #pragma unroll 1
@@ -395,15 +402,16 @@ std::atomic<PFN_tmapEncodeTiled> g_encode{nullptr};
 
 template <int BN, int EPI>
 int launch_variant2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKParams& kp, int num_tiles2, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN, EPI>;
   static PerDeviceOnce once;                               // the shared-memory opt-in is a per-device (per-context) attribute
   int rc = once.run([](int) -> int {
-    WB_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM));
+    WB_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     return WB_OK;
   });
   if (rc != WB_OK) return rc;
   int pairs = device_sm_count() / 2;
   if (num_tiles2 < pairs) pairs = num_tiles2;
-  gemm2_tn_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM, stream>>>(ta, tb, tc, kp);
+  gemm2_tn_kernel<BN, EPI><<<2 * pairs, Cfg::THREADS, Cfg::SMEM, stream>>>(ta, tb, tc, kp);
   count_launch();
   WB_CUDA_OK(cudaGetLastError());
   return WB_OK;
@@ -478,9 +486,9 @@ static int make_tmap_f32_3d(CUtensorMap* out, void* base, uint64_t d0, uint64_t 
   return WB_OK;
 }
 
-int gemm_tiles_n(int N) {                                   // arrivals per 32-row group on GemmDesc::ready: two epilogue warps per column tile
+int gemm_tiles_n(int N) {                                   // arrivals per 32-row group on GemmDesc::ready: one epilogue warp per column tile
   const int BN = (N % 256 == 0) ? 256 : 128;
-  return 2 * ((N + BN - 1) / BN);
+  return (N + BN - 1) / BN;
 }
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {

@@ -107,11 +107,11 @@ struct GemmDesc {
   int out_row_off;
   const float* pe;            // EPI_GELU_PE_F32: [>=rows_per_batch][N] f32
   // EPI_RESID_F32 with n_batch == 1, optional: ready[r / 32] is incremented once per column tile when that tile's reductions into rows
-  // [32 (r / 32), +32) have been performed (by each of the tile's two epilogue warps) -- a kernel running BESIDE the GEMM (layernorm_follow) picks a row group up as soon as its
+  // [32 (r / 32), +32) have been performed -- a kernel running BESIDE the GEMM (layernorm_follow) picks a row group up as soon as its
   // counter reaches gemm_tiles_n(N) and finds the rows in L2.  nullptr: no signalling.
   unsigned int* ready = nullptr;
 };
-int gemm_tiles_n(int N);      // arrivals on ready[] per row group for a GEMM of N columns (two epilogue warps per column tile)
+int gemm_tiles_n(int N);      // arrivals on ready[] per row group for a residual GEMM of N columns (one per column tile)
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
 int gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
