@@ -192,7 +192,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
   if (warp < 4) {
     reg_dealloc<REGS_ROLE>();
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {                                  // one thread, known to the compiler: descriptors go to uniform registers without waterfall loops
         // ------------------------------------------------------------------ TMA producer
         uint32_t g = 0;                                   // running KV block counter across items
         int it = 0;
@@ -215,7 +215,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         // ------------------------------------------------------------------ S_t = Q_t K^T issuer (both tiles)
         constexpr uint32_t idesc_s = umma_idesc_op16(BQ, BKV, 0);
         constexpr uint32_t idesc_s_tail = umma_idesc_op16(BQ, TAIL_KEYS, 0);     // short tail block: 96 key columns instead of 128
@@ -246,7 +246,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
         }
       }
     } else {
-      if (lane == 0) {
+      if (elect_one()) {
         // ------------------------------------------------------------------ O_t += P_t V issuer, one warp per tile
         constexpr uint32_t idesc_o = umma_idesc_op16(BQ, DH, 1);        // B = V tile, MN-major
         const int t = warp - 2;

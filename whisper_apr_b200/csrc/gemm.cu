@@ -201,7 +201,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int mt = mb - b * tiles_m;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
-        if (lane == 0) {
+        if (elect_one()) {
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
           tma_load_3d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, mt * 2 * BM + static_cast<int>(rank) * BM, b);
           tma_load_3d_2sm(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BK, nb * BN + static_cast<int>(rank) * (BN / 2), 0);
@@ -228,7 +228,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after_sync();
           const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
           const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
-          if (lane == 0) {
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2sm(&empty[stage]);      // frees the stage in both CTAs once these MMAs retire
@@ -236,7 +236,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (lane == 0) umma_commit_2sm(&tfull[buf]);           // accumulators ready for both CTAs' epilogues
+        if (elect_one()) umma_commit_2sm(&tfull[buf]);         // accumulators ready for both CTAs' epilogues
         __syncwarp();
       }
     }
@@ -250,6 +250,33 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int NCH = BN / 32;
     constexpr bool kResid = EPI == EPI_RESID_F32;
     uint32_t it = 0;
+    constexpr int NI = (BN + 32 * EW - 1) / (32 * EW);        // columns per epilogue thread when staging scale / bias
+    float pre_s[NI], pre_b[NI];
+    auto load_sb = [&](int tile_) {
+      const int nb_ = tile_ % p.tiles_n;
+#pragma unroll
+      for (int ii = 0; ii < NI; ++ii) {
+        const int i = ii * 32 * EW + et;
+        const int nn = nb_ * BN + i;
+        const bool ok = i < BN && nn < p.N;
+        pre_s[ii] = ok ? p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + nn) : 1.0f) : 0.f;      // columns past N get 0
+        pre_b[ii] = (ok && p.bias != nullptr) ? __ldg(p.bias + nn) : 0.f;
+      }
+    };
+    auto store_sb = [&](uint32_t b_) {
+#pragma unroll
+      for (int ii = 0; ii < NI; ++ii) {
+        const int i = ii * 32 * EW + et;
+        if (i < BN) {
+          sts_f1(smem_u32(s_scale + b_ * BN) + 4 * i, pre_s[ii]);
+          sts_f1(smem_u32(s_bias + b_ * BN) + 4 * i, pre_b[ii]);
+        }
+      }
+    };
+    if (pair < num_tiles) {
+      load_sb(pair);
+      store_sb(0);
+    }
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
       const uint32_t buf = it & 1u;
       const uint32_t use = it >> 1;
@@ -260,18 +287,13 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int r_in_batch = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
       const bool row_ok = r_in_batch < p.rows_per_batch;
       const long long out_row = static_cast<long long>(b) * p.out_rows_per_batch + p.out_row_off + r_in_batch;
-      // stage this tile's per-column scale (alpha x dequantisation scale) and bias; columns past N get 0
+      // this tile's per-column scale (alpha x dequantisation scale) and bias were stored at the end of the previous tile (or before
+      // the loop); the NEXT tile's are fetched now, so that their L2 round trip runs under this tile's work instead of in front of it
+      // (at K = 512 a tile is 2 us of MMAs: 0.5 us of load latency per tile showed)
       const uint32_t sc = smem_u32(s_scale + buf * BN);      // shared-window addresses: LDS / STS, not generic loads (see lds_f4)
       const uint32_t bi = smem_u32(s_bias + buf * BN);
-#pragma unroll
-      for (int i0 = 0; i0 < BN; i0 += 32 * EW) {
-        const int i = i0 + et;
-        if (BN < 32 * EW && i >= BN) break;
-        const int nn = nb * BN + i;
-        const bool ok = nn < p.N;
-        sts_f1(sc + 4 * i, ok ? p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + nn) : 1.0f) : 0.f);
-        sts_f1(bi + 4 * i, (ok && p.bias != nullptr) ? __ldg(p.bias + nn) : 0.f);
-      }
+      const bool has_next = tile + n_pairs < num_tiles;
+      if (has_next) load_sb(tile + n_pairs);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");          // scale / bias visible to every epilogue warp
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after_sync();
@@ -316,21 +338,28 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr bool kBf16Out = EPI == EPI_BF16 || EPI == EPI_GELU_BF16;
       auto half_bf16 = [&](const uint32_t (&v)[32], int c, int hh) {
         const uint32_t sc4 = sc + c * 128, bi4 = bi + c * 128;
+        // all of the chunk's scale / bias vectors first: the volatile shared-memory loads keep program order, so loading them group by
+        // group in front of their FMAs exposed one LDS latency per 8 columns to an in-order warp
+        float4 s4[8], b4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s4[i] = lds_f4(sc4 + 16 * i); b4[i] = lds_f4(bi4 + 16 * i); }
+        float a[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), s4[i].x, b4[i].x);
+          a[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), s4[i].y, b4[i].y);
+          a[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), s4[i].z, b4[i].z);
+          a[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), s4[i].w, b4[i].w);
+        }
+        if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) a[k] = gelu_tanh_approx(a[k]);     // 32 independent chains: the MUFU.TANH latency hides in the batch
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                         // 8 columns -> one 16 B store
-          const float4 s0 = lds_f4(sc4 + 32 * i), b0 = lds_f4(bi4 + 32 * i), s1 = lds_f4(sc4 + 32 * i + 16), b1 = lds_f4(bi4 + 32 * i + 16);
-          float a[8];
-          a[0] = fmaf(__uint_as_float(v[8 * i + 0]), s0.x, b0.x); a[1] = fmaf(__uint_as_float(v[8 * i + 1]), s0.y, b0.y);
-          a[2] = fmaf(__uint_as_float(v[8 * i + 2]), s0.z, b0.z); a[3] = fmaf(__uint_as_float(v[8 * i + 3]), s0.w, b0.w);
-          a[4] = fmaf(__uint_as_float(v[8 * i + 4]), s1.x, b1.x); a[5] = fmaf(__uint_as_float(v[8 * i + 5]), s1.y, b1.y);
-          a[6] = fmaf(__uint_as_float(v[8 * i + 6]), s1.z, b1.z); a[7] = fmaf(__uint_as_float(v[8 * i + 7]), s1.w, b1.w);
-          if constexpr (EPI == EPI_GELU_BF16) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = gelu_tanh_approx(a[k]);
-          }
           const uint32_t j = static_cast<uint32_t>(hh * 4 + i);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pack_op16x2(a[0], a[1])),
-                       "r"(pack_op16x2(a[2], a[3])), "r"(pack_op16x2(a[4], a[5])), "r"(pack_op16x2(a[6], a[7]))
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pack_op16x2(a[8 * i + 0], a[8 * i + 1])),
+                       "r"(pack_op16x2(a[8 * i + 2], a[8 * i + 3])), "r"(pack_op16x2(a[8 * i + 4], a[8 * i + 5])), "r"(pack_op16x2(a[8 * i + 6], a[8 * i + 7]))
                        : "memory");
         }
       };
@@ -370,6 +399,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+      if (has_next) store_sb(buf ^ 1u);                       // every warp is past this tile's bar.sync: the other buffer is free
       if constexpr (kResid) {
         // tell the follower (layernorm_follow_kernel on another stream) that this column tile's share of rows row0 .. row0 + 31 is in
         // the residual stream: the reductions are complete (wait_group, not .read), ordered before the counter by the fences

@@ -82,6 +82,20 @@ __device__ __forceinline__ void sts_f1(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// One lane of a converged warp (elect.sync).  Unlike `lane == 0`, the compiler KNOWS a single thread runs the guarded region, so
+// operands that must live in uniform registers (tcgen05.mma / TMA descriptors, mbarrier addresses) are moved with one R2UR instead of a
+// per-distinct-value waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY around every UTCHMMA and UTMALDG: ~130 instructions per k-block
+// in the GEMM's single-warp MMA issuer, more than the 512 cycles the k-block's MMAs take).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
