@@ -243,6 +243,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..9 of both CTAs)
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read (warp id % 4)
+    // ONE elected thread per warp issues this warp's TMA stores / reductions and waits on their bulk groups (groups belong to the
+    // issuing thread, so the election happens once); see elect_one() for why not `lane == 0`
+    const bool leader = elect_one();
     const int half = (warp - 2) >> 2;                       // which share of the tile's column chunks this warp takes (EW / 4 shares)
     const int et = static_cast<int>(threadIdx.x) - 64;      // 0 .. 32 EW - 1 among the epilogue threads
     float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);    // [2][BN]
@@ -311,7 +314,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (kResid) {
           if (row0_in_batch >= p.rows_per_batch) return;      // warp-uniform: nothing of this warp's rows exists
           const uint32_t sc4 = sc + c * 128, bi4 = bi + c * 128;
-          if (lane == 0) tma_store_wait_read<0>();            // the previous chunk's reduction has read the staging tile
+          if (leader) tma_store_wait_read<0>();            // the previous chunk's reduction has read the staging tile
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -324,7 +327,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (leader) {
             tma_reduce_add_3d(&tmC, stage, n0, row0_in_batch, b);
             tma_store_commit();
           }
@@ -374,7 +377,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (kBf16Out) {
           const bool live = nb * BN + c * 32 < p.N && row0_in_batch < p.rows_per_batch;       // warp-uniform
           if (live) {
-            if (lane == 0) tma_store_wait_read<0>();          // the previous pair's store has read the staging tile
+            if (leader) tma_store_wait_read<0>();          // the previous pair's store has read the staging tile
             __syncwarp();
             half_bf16(v0, c, 0);
           }
@@ -384,7 +387,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             half_bf16(v1, c + 1, 1);                          // columns past N (N % 64 == 32) are clipped by the tensor map
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (leader) {
               tma_store_3d(&tmC, stage, nb * BN + c * 32, row0_in_batch, b);
               tma_store_commit();
             }
@@ -398,12 +401,12 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+      if (leader) mbar_arrive_leader(&tempty[buf]);
       if (has_next) store_sb(buf ^ 1u);                       // every warp is past this tile's bar.sync: the other buffer is free
       if constexpr (kResid) {
         // tell the follower (layernorm_follow_kernel on another stream) that this column tile's share of rows row0 .. row0 + 31 is in
         // the residual stream: the reductions are complete (wait_group, not .read), ordered before the counter by the fences
-        if (p.ready != nullptr && row0_in_batch < p.rows_per_batch && lane == 0) {
+        if (p.ready != nullptr && row0_in_batch < p.rows_per_batch && leader) {
           tma_store_wait_all();
           asm volatile("fence.proxy.async;" ::: "memory");
           __threadfence();
@@ -412,7 +415,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     if constexpr (kResid || EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
-      if (lane == 0) tma_store_wait_all();     // every store / reduction of this warp has been performed before the CTA exits
+      if (leader) tma_store_wait_all();     // every store / reduction of this warp has been performed before the CTA exits
     }
   }
 
