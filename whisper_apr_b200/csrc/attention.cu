@@ -65,7 +65,7 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 
 // exponentials of one 128-score row -> packed bf16 pairs (what tcgen05.st writes as P) and the row sum (four partial sums).
 // Measured alternatives that lost (tools/attn_bench.py, 32 x 20 x 1500 x 1500, ms per launch; this form: 0.517):
-// packed FFMA2/FADD2 in batches of 16 (0.625), scale+exponentials only under the token with the pack/sum after it (0.627),
+// packed FFMA2/FADD2 in batches of 16 (0.625) or pair by pair (one FFMA2 + one FADD2 per pair, 5 instead of 7 instructions: 0.597), scale+exponentials only under the token with the pack/sum after it (0.627),
 // a second warpgroup per tile on half the columns (0.69), 1-3 of every 8 exponentials as a polynomial on the FMA pipe (+2..+19 %),
 // a run-time loop over 32-column chunks re-read from TMEM with the pack/sum one iteration behind the exponentials (0.60).
 // a streaming block (exponentials against the previous blocks' reference max, chunk by chunk under the tcgen05.ld of the next chunk,
