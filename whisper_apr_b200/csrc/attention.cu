@@ -51,6 +51,7 @@ struct AttnTmParams {
   float scale_log2;
   op16* out;
   int use_token;
+  int n_chunks, reverse;              // reverse: chunks are walked from the last to the first (the producer's most recent rows first)
   int tail_keys;                      // a last KV block with at most this many keys runs as a 96-key block (0: never)
   uint32_t rt_zero;                   // 0, but only known at run time (exp_row's ordering trick)
 };
@@ -59,7 +60,7 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
   const int qp = item % p.n_qpairs;
   const int r = item / p.n_qpairs;
   h = r % p.n_heads;
-  b = r / p.n_heads;
+  b = p.reverse ? p.n_chunks - 1 - r / p.n_heads : r / p.n_heads;
   q0 = qp * 2 * BQ;
 }
 
@@ -406,7 +407,7 @@ int attention_init() {
   });
 }
 
-int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream) {
+int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream, bool reverse) {
   int rc = attention_init();
   if (rc != WB_OK) return rc;
   if (B <= 0 || S <= 0) return WB_OK;
@@ -421,6 +422,8 @@ int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_head
   p.n_qpairs = (S + 2 * BQ - 1) / (2 * BQ);
   p.n_heads = n_heads;
   p.n_items = B * n_heads * p.n_qpairs;
+  p.n_chunks = B;
+  p.reverse = reverse ? 1 : 0;
   p.scale_log2 = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
   p.out = out;
   static const int no_token = getenv("WB_ATTN_NOTOKEN") != nullptr;       // tuning switch

@@ -74,9 +74,10 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float*
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d,
-                 uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                 uint16_t* __restrict__ out_16, bool as_bf16, float* __restrict__ out_f32, bool reverse) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (reverse) row = rows - 1 - row;                      // last rows first: the ones the producing GEMM left in L2
   ln_row<NV, false>(x, gamma, beta, row, d, threadIdx.x & 31, out_16, as_bf16, out_f32);
 }
 
@@ -264,15 +265,15 @@ inline unsigned grid_for(size_t n) {
 }  // namespace
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, void* out_16v, bool out_16_is_bf16,
-                     float* out_f32, cudaStream_t stream) {
+                     float* out_f32, cudaStream_t stream, bool reverse) {
   uint16_t* out_bf16 = static_cast<uint16_t*>(out_16v);
   if (rows <= 0) return WB_OK;
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
   if (d % 128 == 0 && d <= 2048) {
-    if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
-    else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
-    else layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);
+    if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32, reverse);
+    else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32, reverse);
+    else layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32, reverse);
     count_launch();
   } else {
     layernorm_generic_kernel<<<grid, 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_16_is_bf16, out_f32);

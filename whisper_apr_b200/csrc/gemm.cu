@@ -47,6 +47,7 @@ struct GemmKParams {
   void* out;
   const float* pe;
   unsigned int* ready;          // EPI_RESID_F32: per-32-row completion counters for a follower kernel (or nullptr)
+  int reverse;                  // row tiles are walked from the last to the first (GemmDesc::reverse)
   uint32_t idesc;               // tcgen05 instruction descriptor
 };
 
@@ -196,7 +197,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t phase = 0;
     for (int tile = pair; tile < num_tiles; tile += n_pairs) {
       const int nb = tile % p.tiles_n;
-      const int mb = tile / p.tiles_n;
+      const int mb = p.reverse ? p.n_batch * tiles_m - 1 - tile / p.tiles_n : tile / p.tiles_n;
       const int b = mb / tiles_m;
       const int mt = mb - b * tiles_m;
       for (int kb = 0; kb < kblocks; ++kb) {
@@ -284,7 +285,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t buf = it & 1u;
       const uint32_t use = it >> 1;
       const int nb = tile % p.tiles_n;
-      const int mb = tile / p.tiles_n;
+      const int mb = p.reverse ? p.n_batch * tiles_m - 1 - tile / p.tiles_n : tile / p.tiles_n;
       const int b = mb / tiles_m;
       const int mt = mb - b * tiles_m;
       const int r_in_batch = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
@@ -553,6 +554,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.out = g.out;
   kp.pe = g.pe;
   kp.ready = (g.epilogue == EPI_RESID_F32 && g.n_batch == 1) ? g.ready : nullptr;
+  kp.reverse = g.reverse ? 1 : 0;
   kp.idesc = umma_idesc_op16(2 * BM, BN, 0);
   const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
   CUtensorMap tc = ta;                                    // the f32 debug / positional-embedding epilogues do not read it

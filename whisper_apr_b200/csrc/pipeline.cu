@@ -85,8 +85,18 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   WB_PROF(PC_GEMM, launch_gemm(g, st));
 
   const int M = B * S;
+  // Direction of travel over the rows, flipped after every kernel of a layer (`zig()`): a kernel that walks its rows in the opposite
+  // direction of its producer starts on what the producer wrote last -- the part of a 123-491 MB activation that is still in the
+  // 126 MB L2 -- instead of on what was evicted first.  WB_NO_ZIGZAG=1: every kernel ascending (A/B switch).
+  bool dir = false;
+  auto zig = [&]() -> bool {
+    const bool d0 = dir;
+    if (m->zigzag) dir = !dir;
+    return d0;
+  };
   auto flat = [&](const op16* A, int K, const op16* W, int N, int epi, float alpha, const float* cs, const float* bias, void* out) {
     GemmDesc q{};
+    q.reverse = zig();
     q.A = A; q.a_row_stride = K; q.a_batch_stride = static_cast<long long>(M) * K; q.rows_per_batch = M; q.n_batch = 1;
     q.W = W; q.N = N; q.K = K; q.epilogue = epi; q.alpha = alpha; q.col_scale = cs; q.bias = bias;
     q.out = out; q.ldc = N; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
@@ -119,13 +129,14 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
     q.A = A; q.a_row_stride = K; q.a_batch_stride = static_cast<long long>(M) * K; q.rows_per_batch = M; q.n_batch = 1;
     q.W = W; q.N = d; q.K = K; q.epilogue = EPI_RESID_F32; q.alpha = alpha; q.col_scale = cs; q.bias = bias;
     q.out = w.x.p; q.ldc = d; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
+    q.reverse = follow ? false : zig();
     if (g == nullptr) {                                                             // no LayerNorm behind this one
       WB_PROF(PC_GEMM, launch_gemm(q, st));
       return WB_OK;
     }
     if (!follow) {
       WB_PROF(PC_GEMM, launch_gemm(q, st));
-      WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, g, bta, M, d, w.xn.p, false, nullptr, st));
+      WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, g, bta, M, d, w.xn.p, false, nullptr, st, zig()));
       return WB_OK;
     }
     q.ready = w.ln_ready.p;
@@ -142,10 +153,10 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
   };
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = m->layers[i];
-    if (i == 0) { WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, false, nullptr, st)); }
+    if (i == 0) { WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, false, nullptr, st, zig())); }
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.pqkv, lw.wqkv, 3 * dd)); }
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p));
-    WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st));
+    WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st, zig()));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.po, lw.wo, dd)); }
     if ((rc = resid_then_ln(w.att.p, d, lw.wo, lw.so, lw.cso, lw.bo, lw.ln2_g, lw.ln2_b)) != WB_OK) return rc;
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p1, lw.w1, 4 * dd)); }
@@ -160,7 +171,7 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
     // 16-bit states: bf16 when the caller asked for WB_BF16 (a user-facing format), the operand format when they feed the decoder's
     // cross-attention K/V GEMM (WB_OP16, internal)
     WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, m->lnp_g, m->lnp_b, M, d, out_dtype != WB_F32 ? d_out : nullptr, out_dtype == WB_BF16,
-                                           out_dtype == WB_F32 ? static_cast<float*>(d_out) : nullptr, st));
+                                           out_dtype == WB_F32 ? static_cast<float*>(d_out) : nullptr, st, zig()));
   } else {
     if (out_dtype == WB_BF16) return set_error(WB_ERR_MODEL, "truncated encodes are f32 only");
     if (out_dtype == WB_OP16) rc = launch_f32_to_op16(w.x.p, static_cast<op16*>(d_out), static_cast<size_t>(M) * d, st);

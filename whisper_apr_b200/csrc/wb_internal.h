@@ -110,6 +110,9 @@ struct GemmDesc {
   // [32 (r / 32), +32) have been performed -- a kernel running BESIDE the GEMM (layernorm_follow) picks a row group up as soon as its
   // counter reaches gemm_tiles_n(N) and finds the rows in L2.  nullptr: no signalling.
   unsigned int* ready = nullptr;
+  // walk the row tiles from the last to the first: a kernel that runs in the OPPOSITE direction of its producer starts on the rows
+  // the producer wrote last, i.e. the ones still in the 126 MB L2 (pipeline.cu alternates the direction from kernel to kernel)
+  bool reverse = false;
 };
 int gemm_tiles_n(int N);      // arrivals on ready[] per row group for a residual GEMM of N columns (one per column tile)
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
@@ -118,7 +121,7 @@ int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
 
 // ---- attention: qkv bf16 [B][S][3d] (q | k | v column blocks) -> out bf16 [B][S][d]
-int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream);
+int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream, bool reverse = false);
 int attention_init();
 
 // ---- mel
@@ -172,7 +175,7 @@ int mel_init();
 
 // ---- elementwise / normalisation
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, void* out_16, bool out_16_is_bf16,
-                     float* out_f32, cudaStream_t stream);
+                     float* out_f32, cudaStream_t stream, bool reverse = false);
 // LayerNorm that FOLLOWS a residual GEMM running on another stream: row group g (32 rows) is normalised as soon as ready[g] == need
 // (GemmDesc::ready), read through L2, and the counter is re-armed to 0.  Same arithmetic as launch_layernorm (op16 output only).
 // wait = true: the concurrent form (gives up after 20 ms without progress); wait = false: the sweep behind the GEMM that normalises
