@@ -75,6 +75,12 @@ __device__ __forceinline__ void item_coords(const AttnTmParams& p, int item, int
 // this one's; token as an mbarrier whose arrival the later pairs depend on, placement checked in the SASS) is slower the larger the
 // overlap: 0.531 / 0.546 / 0.595 against 0.499 with exclusive phases and 0.599 with no token at all (profiles/r02l_attn_handover.txt):
 // two warps of one scheduler inside the MUFU phase at the same time cost more than the hand-over they hide.
+// Part of the row as polynomials on the FMA pipe BEFORE the warpgroup takes the token (8 / 16 / 24 of the 64 pairs computed while it
+// would otherwise wait for the other warpgroup's MUFU phase, ordered in front of the barrier through its id operand; the rest on the MUFU
+// behind it) is slower in every form -- 0.616 / 0.547 / 0.609 ms with ptxas free to place the MUFU part, 0.543 / 0.569 / 0.645 with that
+// part pinned behind the barrier, 0.566 pinned with no polynomial at all, against 0.508 (profiles/r02an_attn_prepoly.txt): the waiting
+// warpgroup's FMA work takes issue slots and FMA-pipe cycles from the warpgroup inside the phase, and the placement ptxas finds for the
+// plain form (22 exponentials above the barrier, the hand-over behind the last one) is better than any the dependences can force.
 // ptxas also hoists register-only work above the token's bar.sync; pinning the phase behind a post-barrier shared-memory load
 // made it slower (0.549), and made the two-warpgroups-per-tile variant 0.62 instead of 0.73 -- still behind this form.
 // Where the time is (measured): with every tcgen05.mma skipped the kernel takes 0.460 ms, i.e. the softmax + synchronisation
