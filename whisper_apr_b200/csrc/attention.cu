@@ -110,7 +110,7 @@ __device__ __forceinline__ float exp2_fma_pipe(float x) {
 
 // POLY 0: every exponential on the MUFU; n > 0: one pair in n goes to the FMA pipe instead; n < 0: MUFU only, consumers lag.
 // NP: pairs of the row that exist (64 = a full 128-key block; 48 = the short tail block, whose last 32 columns are never computed).
-template <int POLY, int NP>
+template <int POLY, int NP, bool PBF>     // PBF: P (and Q, K, V) are bf16 -- see launch_attention
 __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk)[64], float c, float mb, uint32_t rt_zero) {
   float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -129,7 +129,7 @@ __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk
         e1 = fast_exp2(x1);
       }
       rs4[i & 3] += e0 + e1;
-      pk[i] = pack_op16x2(e0, e1);
+      pk[i] = PBF ? pack_bf16x2(e0, e1) : pack_op16x2(e0, e1);
     }
   } else {
     // consumers LAG = -POLY pairs behind their exponentials, with a true dependence that keeps ptxas from re-pairing them: the sum of
@@ -149,14 +149,14 @@ __device__ __forceinline__ float exp_row(const uint32_t (&s)[128], uint32_t (&pk
         // dependence -- the sum of pair j is ordered after the exponentials of pair i = j + LAG
         if (i < NP) b = __uint_as_float(__float_as_uint(b) | (__float_as_uint(e[2 * i + 1]) & rt_zero));
         rs4[j & 3] += e[2 * j] + b;
-        pk[j] = pack_op16x2(e[2 * j], e[2 * j + 1]);
+        pk[j] = PBF ? pack_bf16x2(e[2 * j], e[2 * j + 1]) : pack_op16x2(e[2 * j], e[2 * j + 1]);
       }
     }
   }
   return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 }
 
-template <int POLY>
+template <int POLY, bool PBF = false>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -224,8 +224,9 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
     } else if (warp == 1) {
       if (elect_one()) {
         // ------------------------------------------------------------------ S_t = Q_t K^T issuer (both tiles)
-        constexpr uint32_t idesc_s = umma_idesc_op16(BQ, BKV, 0);
-        constexpr uint32_t idesc_s_tail = umma_idesc_op16(BQ, TAIL_KEYS, 0);     // short tail block: 96 key columns instead of 128
+        constexpr uint32_t kFmt = PBF ? 1u : kIdescOp16Fmt;
+        constexpr uint32_t idesc_s = umma_idesc_16(BQ, BKV, 0, kFmt);
+        constexpr uint32_t idesc_s_tail = umma_idesc_16(BQ, TAIL_KEYS, 0, kFmt);     // short tail block: 96 key columns instead of 128
         const bool short_tail = p.S - (n - 1) * BKV <= p.tail_keys;
         uint32_t g = 0;
         int it = 0;
@@ -255,7 +256,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
     } else {
       if (elect_one()) {
         // ------------------------------------------------------------------ O_t += P_t V issuer, one warp per tile
-        constexpr uint32_t idesc_o = umma_idesc_op16(BQ, DH, 1);        // B = V tile, MN-major
+        constexpr uint32_t idesc_o = umma_idesc_16(BQ, DH, 1, PBF ? 1u : kIdescOp16Fmt);        // B = V tile, MN-major
         const int t = warp - 2;
         const uint32_t tO = tmem_base + COL_O + t * 64;
         const uint32_t tP = tmem_base + COL_P + t * 64;
@@ -348,7 +349,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTmParam
         // ping-pong token: MUFU phases of the two warpgroups alternate
         if (p.use_token) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
         uint32_t pk[64];
-        const float rsum = exp_row<POLY, NCOL / 2>(s, pk, c, mb, p.rt_zero);
+        const float rsum = exp_row<POLY, NCOL / 2, PBF>(s, pk, c, mb, p.rt_zero);
         if (p.use_token && !(t == 1 && g + 1 == total_blocks)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // hand the token over
         l_run = l_run * alpha + rsum;
         if (!pv_ok) mbar_wait(&pv_done[t], (g - 1) & 1u);    // PV of the previous block has read P_t
@@ -409,11 +410,12 @@ int attention_init() {
     WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
     WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
     WB_CUDA_OK(cudaFuncSetAttribute(attention_tm_kernel<-2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+    WB_CUDA_OK((cudaFuncSetAttribute(attention_tm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM)));
     return WB_OK;
   });
 }
 
-int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream, bool reverse) {
+int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream, bool reverse, bool qkv_bf16) {
   int rc = attention_init();
   if (rc != WB_OK) return rc;
   if (B <= 0 || S <= 0) return WB_OK;
@@ -445,6 +447,16 @@ int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_head
   // distance shortens the phase: it runs at ~81 % of the MUFU pipe's rate at the clock of the run (2530 of 2048 cycles per 256 x 128
   // scores) and the remainder is the hand-over between the two alternating warpgroups, not the instruction mix inside the phase.
   static const int poly = getenv("WB_ATTN_POLY") ? atoi(getenv("WB_ATTN_POLY")) : 0;
+  if (qkv_bf16 && poly == 0) {
+    // Q, K, V arrive as bf16 and P is packed as bf16: both products run as bf16 MMAs, the output is still written in the operand format
+    // (it feeds out_proj).  In an fp16-operand build this is the one place where bf16 costs nothing in accuracy -- no weights are involved;
+    // CPU emulation at depth 32: max-abs 2.79e-3 against 2.58e-3 -- and its MMAs draw less power under the board's cap.
+    attention_tm_kernel<0, true><<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p);
+    count_launch();
+    WB_CUDA_OK(cudaGetLastError());
+    return WB_OK;
+  }
+  if (qkv_bf16 && kOp16IsFp16) return set_error(WB_ERR_MODEL, "the attention tuning variants take operand-format q, k, v");
   switch (poly) {
     case 8: attention_tm_kernel<8><<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p); break;
     case -2: attention_tm_kernel<-2><<<grid, TM_THREADS, TM_SMEM, stream>>>(tm, p); break;

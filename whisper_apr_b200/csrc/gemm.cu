@@ -48,6 +48,7 @@ struct GemmKParams {
   const float* pe;
   unsigned int* ready;          // EPI_RESID_F32: per-32-row completion counters for a follower kernel (or nullptr)
   int reverse;                  // row tiles are walked from the last to the first (GemmDesc::reverse)
+  int out_bf16;                 // 16-bit outputs are packed as bf16 whatever the operand format (GemmDesc::out_bf16)
   uint32_t idesc;               // tcgen05 instruction descriptor
 };
 
@@ -359,11 +360,19 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 32; ++k) a[k] = gelu_tanh_approx(a[k]);     // 32 independent chains: the MUFU.TANH latency hides in the batch
         }
+        uint32_t pk[16];
+        if (p.out_bf16) {                                     // warp-uniform
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(a[2 * i], a[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_op16x2(a[2 * i], a[2 * i + 1]);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                         // 8 columns -> one 16 B store
           const uint32_t j = static_cast<uint32_t>(hh * 4 + i);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pack_op16x2(a[8 * i + 0], a[8 * i + 1])),
-                       "r"(pack_op16x2(a[8 * i + 2], a[8 * i + 3])), "r"(pack_op16x2(a[8 * i + 4], a[8 * i + 5])), "r"(pack_op16x2(a[8 * i + 6], a[8 * i + 7]))
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((j ^ (lane & 7u)) << 4)), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                       "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
                        : "memory");
         }
       };
@@ -555,6 +564,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.pe = g.pe;
   kp.ready = (g.epilogue == EPI_RESID_F32 && g.n_batch == 1) ? g.ready : nullptr;
   kp.reverse = g.reverse ? 1 : 0;
+  kp.out_bf16 = g.out_bf16 ? 1 : 0;
   kp.idesc = umma_idesc_op16(2 * BM, BN, 0);
   const int num_tiles2 = kp.n_batch * ((g.rows_per_batch + 2 * BM - 1) / (2 * BM)) * kp.tiles_n;
   CUtensorMap tc = ta;                                    // the f32 debug / positional-embedding epilogues do not read it

@@ -293,6 +293,7 @@ int load_replica(Replica* m, const AprFile& f, const uint8_t* /*pinned_base*/) {
   DeviceGuard guard(m->device);
   m->cfg = f.cfg;
   m->use_graphs = getenv("WB_NO_GRAPH") == nullptr;       // A/B switch: plain launches instead of graph replay
+  m->attn_bf16 = getenv("WB_ATTN_FP16") == nullptr;      // A/B switch: attention operands in the build's operand format instead of bf16
   m->zigzag = getenv("WB_NO_ZIGZAG") == nullptr;         // A/B switch: alternate the row direction from kernel to kernel (L2 reuse)
   m->ln_follow = getenv("WB_LN_FOLLOW") != nullptr;       // experiment switch (default off): LayerNorm as a concurrent follower of the residual GEMMs
   if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) return set_error(WB_ERR_CUDA, "cudaStreamCreate failed");

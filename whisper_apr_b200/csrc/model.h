@@ -133,6 +133,7 @@ struct Replica {
   // the LayerNorm that follows a residual GEMM runs beside it on this stream (fork / join through the two events)
   cudaStream_t ln_stream = nullptr;
   cudaEvent_t ln_fork = nullptr, ln_join = nullptr;
+  bool attn_bf16 = true;                // q, k, v and P in bf16 inside an fp16-operand build (WB_ATTN_FP16=1: operand format)
   bool zigzag = true;                   // WB_NO_ZIGZAG=1: every kernel walks its rows ascending (A/B switch, pipeline.cu)
   bool ln_follow = false;               // WB_LN_FOLLOW=1 / wb_debug_set_ln_follow: experiment, measured slower under the power cap
   int max_batch = 32;

@@ -94,9 +94,11 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
     if (m->zigzag) dir = !dir;
     return d0;
   };
+  bool qkv_out_bf16 = false;
   auto flat = [&](const op16* A, int K, const op16* W, int N, int epi, float alpha, const float* cs, const float* bias, void* out) {
     GemmDesc q{};
     q.reverse = zig();
+    q.out_bf16 = qkv_out_bf16;
     q.A = A; q.a_row_stride = K; q.a_batch_stride = static_cast<long long>(M) * K; q.rows_per_batch = M; q.n_batch = 1;
     q.W = W; q.N = N; q.K = K; q.epilogue = epi; q.alpha = alpha; q.col_scale = cs; q.bias = bias;
     q.out = out; q.ldc = N; q.out_rows_per_batch = M; q.out_row_off = 0; q.pe = nullptr;
@@ -155,8 +157,10 @@ int encode_device(Replica* m, int B, int T, void* d_out, wb_dtype out_dtype, int
     const LayerW& lw = m->layers[i];
     if (i == 0) { WB_PROF(PC_LAYERNORM, launch_layernorm(w.x.p, lw.ln1_g, lw.ln1_b, M, d, w.xn.p, false, nullptr, st, zig())); }
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.pqkv, lw.wqkv, 3 * dd)); }
+    qkv_out_bf16 = m->attn_bf16;                            // q, k, v leave the QKV product as bf16: the attention's two products involve no weights
     WB_PROF(PC_GEMM, flat(w.xn.p, d, lw.wqkv, 3 * d, EPI_BF16, 1.f, lw.sqkv, lw.bqkv, w.qkv.p));
-    WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st, zig()));
+    qkv_out_bf16 = false;
+    WB_PROF(PC_ATTENTION, launch_attention(w.qkv.p, w.att.p, B, S, d, H, st, zig(), m->attn_bf16));
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.po, lw.wo, dd)); }
     if ((rc = resid_then_ln(w.att.p, d, lw.wo, lw.so, lw.cso, lw.bo, lw.ln2_g, lw.ln2_b)) != WB_OK) return rc;
     if (m->quant) { WB_PROF(PC_OTHER, expand(lw.p1, lw.w1, 4 * dd)); }

@@ -303,6 +303,11 @@ constexpr uint32_t kIdescOp16Fmt = 1u;
 #else
 constexpr uint32_t kIdescOp16Fmt = 0u;
 #endif
+// fmt: 0 = fp16, 1 = bf16 (both operands)
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int b_mn_major, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_op16(int M, int N, int b_mn_major) {
   return (1u << 4) | (kIdescOp16Fmt << 7) | (kIdescOp16Fmt << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);

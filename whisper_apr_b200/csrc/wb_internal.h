@@ -113,6 +113,8 @@ struct GemmDesc {
   // walk the row tiles from the last to the first: a kernel that runs in the OPPOSITE direction of its producer starts on the rows
   // the producer wrote last, i.e. the ones still in the 126 MB L2 (pipeline.cu alternates the direction from kernel to kernel)
   bool reverse = false;
+  // EPI_BF16 / EPI_GELU_BF16: store the 16-bit output as bf16 even in an fp16-operand build (the QKV product feeding a bf16 attention)
+  bool out_bf16 = false;
 };
 int gemm_tiles_n(int N);      // arrivals on ready[] per row group for a residual GEMM of N columns (one per column tile)
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
@@ -121,7 +123,8 @@ int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
 
 // ---- attention: qkv bf16 [B][S][3d] (q | k | v column blocks) -> out bf16 [B][S][d]
-int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream, bool reverse = false);
+// qkv_bf16: q, k, v hold bf16 whatever the build's operand format is (GemmDesc::out_bf16 on the QKV GEMM); out is always op16
+int launch_attention(const op16* qkv, op16* out, int B, int S, int d, int n_heads, cudaStream_t stream, bool reverse = false, bool qkv_bf16 = false);
 int attention_init();
 
 // ---- mel
