@@ -10,6 +10,10 @@
 //   .encode_batch_padded(mels)                      Encoder::forward_batch_padded    src/model/encoder.rs:625-660 (BatchEncoderOutput)
 //   .mel_encode_batch(chunks)                       transcribe_batch_optimized 1-2   src/lib.rs:1162-1170
 //   .transcribe_tokens_batch(chunks, prompt, n)     transcribe_batch_optimized 1-3   src/lib.rs:1162-1201 (token ids)
+//   .parse_wav(bytes) / .ingest_wav_16k(bytes)      audio::wav::parse_wav            src/audio/wav.rs:99-293 (+ SincResampler to 16 kHz)
+//   .resample(audio, from, to)                      SincResampler::resample          src/audio/resampler.rs:136-250
+//   .vad_detect(streams)                            VoiceActivityDetector::detect    src/vad.rs:554-700 (VadConfig::default())
+//   .stream_encode_views(streams, size, overlap)    split_into_chunks + compute_mel + forward_batch, chunks read in place
 //   wb::split_into_chunks(n, size, overlap)         audio::split_into_chunks         src/audio/batch.rs:219-240
 //   wb::WhisperError { kind, what() }               WhisperError::{Audio,Model,Format}  src/error.rs:6-44   (Result<T, WhisperError> -> throw)
 //   wb::device_count()                              parallel::thread_count           src/parallel.rs:155-170
@@ -173,6 +177,76 @@ class WhisperApr {
     std::vector<size_t> ln(B);
     for (int i = 0; i < B; ++i) { p[i] = chunks[i].data(); ln[i] = chunks[i].size(); }
     check(wb_mel_encode_batch(h_, p.data(), ln.data(), B, out.data(), WB_F32));
+    return out;
+  }
+
+  // ---- ingest in front of the path and the streaming front end (8f-3)
+  // WavData (wav.rs:40-60): mono f32 samples + what the header said
+  struct WavData {
+    std::vector<float> samples;
+    wb_wav_info info{};
+  };
+  WavData parse_wav(const uint8_t* bytes, size_t n_bytes) const {
+    WavData w;
+    check(wb_wav_parse(bytes, n_bytes, &w.info));
+    w.samples.resize(static_cast<size_t>(w.info.n_frames));
+    check(wb_wav_decode(h_, bytes, n_bytes, w.samples.data(), w.samples.size(), &w.info));
+    return w;
+  }
+  // WAV bytes -> mono -> 16 kHz (what compute_mel is fed from a file)
+  WavData ingest_wav_16k(const uint8_t* bytes, size_t n_bytes) const {
+    WavData w;
+    check(wb_wav_parse(bytes, n_bytes, &w.info));
+    w.samples.resize(wb_resample_len(static_cast<size_t>(w.info.n_frames), w.info.sample_rate, 16000) + 1);
+    size_t n = 0;
+    check(wb_ingest_wav_16k(h_, bytes, n_bytes, w.samples.data(), w.samples.size(), &n, &w.info));
+    w.samples.resize(n);
+    return w;
+  }
+  std::vector<float> resample(const float* audio, size_t n, uint32_t source_rate, uint32_t target_rate) const {
+    std::vector<float> out(wb_resample_len(n, source_rate, target_rate) + 1);
+    size_t n_out = 0;
+    check(wb_resample(h_, audio, n, source_rate, target_rate, out.data(), out.size(), &n_out));
+    out.resize(n_out);
+    return out;
+  }
+  // SpeechSegment (vad.rs:80-100): start / end in seconds, mean energy
+  struct SpeechSegment { float start, end, energy; };
+  std::vector<std::vector<SpeechSegment>> vad_detect(const std::vector<std::vector<float>>& streams, const wb_vad_config* cfg = nullptr,
+                                                     int seg_capacity = 64) const {
+    const int B = static_cast<int>(streams.size());
+    std::vector<std::vector<SpeechSegment>> out(B);
+    if (B == 0) return out;
+    std::vector<const float*> p(B);
+    std::vector<size_t> ln(B);
+    for (int i = 0; i < B; ++i) { p[i] = streams[i].data(); ln[i] = streams[i].size(); }
+    std::vector<float> seg(static_cast<size_t>(B) * seg_capacity * 3);
+    std::vector<int> cnt(B);
+    check(wb_vad_detect_batch(h_, p.data(), ln.data(), B, cfg, seg.data(), seg_capacity, cnt.data(), nullptr, nullptr));
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < std::min(cnt[b], seg_capacity); ++i) {
+        const float* q = seg.data() + (static_cast<size_t>(b) * seg_capacity + i) * 3;
+        out[b].push_back({q[0], q[1], q[2]});
+      }
+    return out;
+  }
+  // every chunk of every stream (views into the uploaded streams) -> [total chunks][1500][d]; counts[i] = chunks of stream i
+  std::vector<float> stream_encode_views(const std::vector<std::vector<float>>& streams, size_t chunk_size, size_t overlap,
+                                         std::vector<size_t>* counts = nullptr) const {
+    const int n = static_cast<int>(streams.size());
+    std::vector<const float*> p(n);
+    std::vector<size_t> ln(n), cnt(n);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+      p[i] = streams[i].data();
+      ln[i] = streams[i].size();
+      total += wb_split_into_chunks(ln[i], chunk_size, overlap, nullptr, nullptr, 0);
+    }
+    std::vector<float> out(total * N_POS_30S * config().n_audio_state);
+    size_t got = 0;
+    if (n) check(wb_stream_encode_views(h_, p.data(), ln.data(), n, chunk_size, overlap, out.data(), WB_F32, total, cnt.data(), &got));
+    out.resize(got * N_POS_30S * config().n_audio_state);
+    if (counts) *counts = cnt;
     return out;
   }
 

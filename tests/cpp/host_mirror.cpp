@@ -88,6 +88,22 @@ int main(int argc, char** argv) {
     }
     EXPECT(model.mel_filterbank_compute(audio.data(), 100).empty());
     EXPECT(model.mel_filterbank_compute(audio.data(), 16000).size() == 98u * cfg.n_mels);       // mel.rs:660-668
+    // ingest + streaming rows through the same mirror: resample 8 kHz -> 16 kHz (length law of SincResampler: ceil(n * to / from)), VAD on
+    // silence (no segments), two 5 s chunks with 0.5 s overlap of the first 9.5 s read in place as views
+    {
+      const std::vector<float> lo(audio.begin(), audio.begin() + 8000);
+      const auto up = model.resample(lo.data(), lo.size(), 8000, 16000);
+      EXPECT(up.size() == 16000u);
+      write_file(prefix + ".resampled", up);
+      const auto segs = model.vad_detect({std::vector<float>(16000, 0.f)});
+      EXPECT(segs.size() == 1 && segs[0].empty());
+      std::vector<size_t> counts;
+      const std::vector<float> stream(audio.begin(), audio.begin() + 152000);
+      const auto views = model.stream_encode_views({stream}, 80000, 8000, &counts);
+      EXPECT(counts.size() == 1 && counts[0] == 2);
+      EXPECT(views.size() == 2u * 1500u * cfg.n_audio_state);
+      write_file(prefix + ".views", views);
+    }
     if (model.has_decoder()) {
       const auto toks = model.transcribe_tokens_batch({audio}, {50258, 50259, 50359, 50363}, 12);
       write_file(prefix + ".tokens", toks[0]);

@@ -49,6 +49,12 @@ def test_cpp_mirror_matches_ctypes_mirror(tmp_path):
     states = np.fromfile(tmp_path / "out.states", np.float32).reshape(2, 1500, cfg.n_audio_state)
     ref = model.mel_encode_batch([audio, audio[: audio.size // 2]])
     assert np.array_equal(states, ref)
+    from whisper_apr_b200 import api
+    up = np.fromfile(tmp_path / "out.resampled", np.float32)
+    assert np.array_equal(up, api.SincResampler(model, 8000, 16000).resample(audio[:8000]))
+    views = np.fromfile(tmp_path / "out.views", np.float32).reshape(2, 1500, cfg.n_audio_state)
+    ref_views, counts = api.stream_encode_views(model, [audio[:152000]], 80000, 8000)
+    assert list(counts) == [2] and np.array_equal(views, ref_views)
     toks = np.fromfile(tmp_path / "out.tokens", np.int32).tolist()
     assert toks == model.transcribe_tokens_batch([audio], D.initial_tokens(), 12)[0]
     model.close()
