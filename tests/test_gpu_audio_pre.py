@@ -197,3 +197,40 @@ def test_streaming_config4_shape_int4_views(fb80):
         ref = E.forward_mel(M.compute_mel(chunks[k], fb80), w, E.CONFIGS["tiny"], attention=E.naive_attention)
         assert np.abs(out[k] - ref).max() <= 2e-2
     model.close()
+
+
+# ---- the reference's own WAV fixtures (demos/test-audio/; wav.rs:949-988, tests/cli_parity_tests.rs:28): real speech through every stage
+def _ref_wav(name):
+    import os
+    return open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_wav_{name}.wav"), "rb").read()
+
+
+@pytest.mark.parametrize("name", ["test-speech-1.5s", "test-8k", "test-24bit", "test-32f", "test-300ms"])
+def test_reference_wav_fixtures_decode_bit_exact(tiny, name):
+    wav = _ref_wav(name)
+    ref = A.parse_wav(wav)
+    got = api.parse_wav(tiny, wav)
+    assert (got.sample_rate, got.original_channels, got.bits_per_sample) == (ref.sample_rate, ref.original_channels, ref.bits_per_sample)
+    assert np.array_equal(got.samples, ref.samples)
+
+
+def test_reference_speech_through_ingest_mel_and_encoder(tiny):
+    """Real speech (the reference's 1.5 s sample and its 8 kHz rendering): WAV -> 16 kHz -> log-mel -> encoder against the oracle at the
+    path's gates: resampler 1e-6, mel 1e-4, encoder 2e-2 / 0.9999."""
+    from oracle import encoder as E
+    cfg = synth.CONFIGS["tiny"]
+    _, tensors = synth.random_model_apr(cfg, seed=0)
+    fb = synth.load_filterbank(cfg.n_mels)
+    got16, _ = api.ingest_wav_16k(tiny, _ref_wav("test-8k"))
+    ref16 = A.resample(A.parse_wav(_ref_wav("test-8k")).samples, 8000, 16000)
+    assert got16.shape == ref16.shape and np.abs(got16 - ref16).max() <= 1e-6
+    speech = A.parse_wav(_ref_wav("test-speech-1.5s")).samples
+    mel = tiny.compute_mel(speech)
+    ref_mel = M.compute_mel(speech, fb)
+    assert mel.shape == ref_mel.shape == (3000, cfg.n_mels)
+    assert np.abs(mel - ref_mel).max() <= 1e-4
+    out = tiny.mel_encode_batch([speech])[0]
+    ref = E.forward_mel(ref_mel, dict(tensors), E.CONFIGS["tiny"], attention=E.naive_attention)
+    err = float(np.abs(out - ref).max())
+    cos = float((out.astype(np.float64) * ref).sum() / (np.linalg.norm(out.astype(np.float64)) * np.linalg.norm(ref)))
+    assert err <= 2e-2 and cos >= 0.9999, (err, cos)
