@@ -214,6 +214,12 @@ def test_reference_wav_fixtures_decode_bit_exact(tiny, name):
     assert np.array_equal(got.samples, ref.samples)
 
 
+def test_device_wav_decode_reproduces_reference_golden_trace(tiny, golden_audio):
+    """The reference's own decode of test-speech-1.5s.wav (test_data/ref_a_audio.bin) from the device's WAV path, bit for bit."""
+    got = api.parse_wav(tiny, _ref_wav("test-speech-1.5s"))
+    assert np.array_equal(got.samples, np.asarray(golden_audio, np.float32))
+
+
 def test_reference_speech_through_ingest_mel_and_encoder(tiny):
     """Real speech (the reference's 1.5 s sample and its 8 kHz rendering): WAV -> 16 kHz -> log-mel -> encoder against the oracle at the
     path's gates: resampler 1e-6, mel 1e-4, encoder 2e-2 / 0.9999."""

@@ -189,3 +189,15 @@ def test_reference_wav_fixtures_parse():
     assert np.corrcoef(up[200:-200], speech.samples[200:-200])[0, 1] > 0.95
     short = A.parse_wav(_ref_wav("test-300ms"))
     assert (short.sample_rate, short.samples.size) == (16000, 4800)
+
+
+def test_wav_oracle_pinned_on_reference_golden_trace(golden_audio):
+    """test_data/ref_a_audio.bin is the REFERENCE's own decode of demos/test-audio/test-speech-1.5s.wav (reference_summary.json:
+    step_a_audio, source = that file; the mel goldens start from it): the oracle's parse_wav of the same file must reproduce it bit for
+    bit, and the statistics the reference recorded for it."""
+    got = A.parse_wav(_ref_wav("test-speech-1.5s")).samples
+    assert got.dtype == np.float32 and np.array_equal(got, np.asarray(golden_audio, np.float32))
+    # test_data/reference_summary.json, step_a_audio
+    assert float(got.min()) == -0.198333740234375 and float(got.max()) == 0.2979736328125
+    assert abs(float(got.std()) - 0.06962854415178299) < 1e-9 and int(np.count_nonzero(got)) == 23980
+    assert abs(float(got.astype(np.float64).mean()) - 0.00017776997992768884) < 1e-8
