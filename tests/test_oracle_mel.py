@@ -117,3 +117,44 @@ def test_to_padded_tensor():
     t = M.to_padded_tensor([a, b], 2)                                                  # batch.rs:107-127
     assert t.shape == (2, 2, 3)
     assert np.array_equal(t[0], a.T) and np.array_equal(t[1, :, :2], b.T) and (t[1, :, 2] == 0).all()
+
+
+def test_prelog_pipeline_reproduces_reference_recorded_run():
+    """test_data/mel_spectrogram.json opens with the recorded stdout of the reference's own `examples/mel_spectrogram` run:
+    MelFilterbank::new(80, 400, 16000) (the HTK fallback bank, mel.rs:58-79,144-212) and MelFilterbank::compute on six
+    deterministic signals, with `Frames` and `Total energy` = sum over mel bins of the frame-mean of |log-mel|.  That run
+    predates today's log10 / clamp / scale tail (it printed |ln(max(E, 1e-10))|: silence gives 23.0259 = ln 1e10 per bin), so
+    it pins everything IN FRONT of the logarithm -- HTK bank construction, periodic Hann, framing, 400-point FFT, power,
+    filterbank product -- on numbers the reference itself produced.  The signals are rebuilt in f32 exactly as
+    examples/mel_spectrogram.rs:50-103 builds them (the chaotic "white noise" included)."""
+    sr = 16000
+    fb = M.htk_filterbank(80).astype(np.float64)
+    w = M.hann_window_periodic().astype(np.float64)
+    i = np.arange(sr, dtype=np.float32)
+    t = (i / np.float32(sr)).astype(np.float32)
+    two_pi = np.float32(2.0) * np.float32(np.pi)
+
+    def tone(f):
+        return (np.sin((two_pi * np.float32(f) * t).astype(np.float32)).astype(np.float32) * np.float32(0.5)).astype(np.float32)
+
+    x = (np.sin((i * np.float32(12345.6789)).astype(np.float32)).astype(np.float32) * np.float32(43758.5453)).astype(np.float32)
+    noise = (((x - np.trunc(x)) * np.float32(2.0) - np.float32(1.0)) * np.float32(0.3)).astype(np.float32)
+    harm = ((np.sin(two_pi * np.float32(150) * t) + np.sin(two_pi * np.float32(300) * t) * np.float32(0.5) +
+             np.sin(two_pi * np.float32(450) * t) * np.float32(0.25) + np.sin(two_pi * np.float32(600) * t) * np.float32(0.125)) * np.float32(0.3)).astype(np.float32)
+
+    def total(audio):
+        n = M.n_frames_for(len(audio))
+        idx = (np.arange(n) * 160)[:, None] + np.arange(400)[None, :]
+        spec = np.fft.rfft(audio[idx].astype(np.float64) * w, axis=1)
+        energy = (spec.real ** 2 + spec.imag ** 2) @ fb.T
+        return n, float(np.abs(np.log(np.maximum(energy, 1e-10))).mean(0).sum())
+
+    recorded = [("silence", np.zeros(sr, np.float32), 1842.0702, 2e-5), ("200 Hz", tone(200), 1521.4725, 2e-5), ("1000 Hz", tone(1000), 1296.1965, 2e-5),
+                ("4000 Hz", tone(4000), 1104.2760, 2e-5), ("white noise", noise, 308.0254, 2e-5), ("speech-like", harm, 1164.4906, 1e-3)]
+    for name, audio, ref_total, tol in recorded:
+        n, tot = total(audio)
+        assert n == 98, name                                                       # "Frames: 98"
+        assert abs(tot - ref_total) <= tol * ref_total, (name, tot, ref_total)
+    # "Mel scale examples" of the same run (hz_to_mel / mel_to_hz, mel.rs:144-160)
+    for hz, mel in [(100.0, 150.49), (500.0, 607.45), (1000.0, 999.99), (2000.0, 1521.36), (4000.0, 2146.06), (8000.0, 2840.02)]:
+        assert abs(float(M.hz_to_mel(hz)) - mel) < 0.006 and abs(float(M.mel_to_hz(M.hz_to_mel(hz))) - hz) < 0.01
